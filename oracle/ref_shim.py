@@ -1,0 +1,78 @@
+"""Import shim that lets the UNMODIFIED reference hot-path functions run in this container.
+
+TEST INFRASTRUCTURE ONLY.  Used by ``oracle/make_golden.py`` (fixture generation) and by
+``tests/test_oracle_vs_reference.py`` (which skips when ``/root/reference`` is absent, as on the
+GPU box).  Nothing in the product path (``leida-python_b200/``) may import this module.
+
+Why a shim: every hot module of the reference imports plotting /
+neuro-imaging packages at top level (``pyleida/signal_tools/_signal_tools.py:2-3,6``,
+``pyleida/clustering/_clustering.py:4-5``, ``pyleida/dynamics_metrics/_dynamics_metrics.py:4-5``)
+that are not installed here, and ``pyleida/dynamics_metrics/_dynamics_metrics.py:250`` uses
+``np.float_`` which NumPy 2 removed.  The shim stubs those imports and restores the alias; no
+reference file is copied or edited.
+"""
+import importlib
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+REFERENCE_ROOT = os.environ.get("LEIDA_REFERENCE_ROOT", "/root/reference")
+
+_STUBS = [
+    "matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm", "matplotlib.patches",
+    "matplotlib.lines", "matplotlib.gridspec", "matplotlib.ticker", "matplotlib.animation",
+    "matplotlib.collections", "matplotlib.figure", "matplotlib.axes",
+    "seaborn", "imageio", "nibabel",
+    "nilearn", "nilearn.signal", "nilearn.plotting", "nilearn.datasets", "nilearn.surface",
+    "nilearn.image", "nilearn.maskers", "nilearn.input_data",
+    "mpl_toolkits", "mpl_toolkits.mplot3d", "mpl_toolkits.axes_grid1",
+]
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyleida"))
+
+
+def load_reference():
+    """Return a namespace holding the reference's hot-path callables (unmodified code)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import numpy as np
+    if not hasattr(np, "float_"):
+        np.float_ = np.float64
+    for name in _STUBS:
+        if name not in sys.modules:
+            sys.modules[name] = MagicMock(name=name)
+    # Load the reference under a private top-level name so that it can never shadow (or be
+    # shadowed by) the product package, which is also called ``pyleida``.
+    saved = {k: v for k, v in sys.modules.items() if k == "pyleida" or k.startswith("pyleida.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        st = importlib.import_module("pyleida.signal_tools._signal_tools")
+        cl = importlib.import_module("pyleida.clustering._clustering")
+        dm = importlib.import_module("pyleida.dynamics_metrics._dynamics_metrics")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        ref_mods = {k: v for k, v in sys.modules.items() if k == "pyleida" or k.startswith("pyleida.")}
+        for k in ref_mods:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    ns = types.SimpleNamespace(
+        hilbert_phase=st.hilbert_phase,
+        phase_coherence=st.phase_coherence,
+        get_eigenvectors=st.get_eigenvectors,
+        KMeansLeida=cl.KMeansLeida,
+        identify_states=cl.identify_states,
+        fractional_occupancy=dm.fractional_occupancy,
+        fractional_occupancy_group=dm.fractional_occupancy_group,
+        dwell_times=dm.dwell_times,
+        dwell_times_group=dm.dwell_times_group,
+        transition_probabilities=dm.transition_probabilities,
+        transition_probabilities_group=dm.transition_probabilities_group,
+        compute_dynamics_metrics=dm.compute_dynamics_metrics,
+        _modules=(st, cl, dm),
+    )
+    return ns
