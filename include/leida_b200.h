@@ -1,0 +1,207 @@
+/*
+ * leida_b200.h -- C-ABI of the B200-native LEiDA hot path (libleida_b200.so).
+ *
+ * The reference (pyleida 1.0) is pure Python and has no FFI of its own; its "operator interface"
+ * for this path is the Python call surface listed in SURVEY.md section 8b.  Each entry point below
+ * names the reference function (file:line under /root/reference/pyleida) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a pyleida maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host";
+ *   - the caller owns all memory (inputs, outputs, workspaces); nothing here allocates or frees;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     keeps no global state besides a thread-local error string;
+ *   - return value: 0 = ok, <0 = error (see LEIDA_ERR_*); leida_last_error() explains.
+ *   - "pitch" arguments are in ELEMENTS of the array's type.
+ */
+#ifndef LEIDA_B200_H
+#define LEIDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEIDA_OK                 0
+#define LEIDA_ERR_INVALID       -1   /* bad argument */
+#define LEIDA_ERR_UNSUPPORTED   -2   /* size outside what the kernels handle */
+#define LEIDA_ERR_CUDA          -3   /* launch / runtime failure */
+#define LEIDA_ERR_WORKSPACE     -4   /* workspace too small */
+
+typedef void* leida_stream_t;
+
+int         leida_version(void);
+const char* leida_last_error(void);
+/* number of SMs of the current device (grid sizing is derived from it) */
+int         leida_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1 -- hilbert_phase          (signal_tools/_signal_tools.py:24-44)
+ * n_series real series of length T (row i at x + i*x_pitch) -> instantaneous phase in (-pi, pi].
+ * Only volumes [t_begin, t_begin+t_count) are written, to phase + i*phase_pitch + (t - t_begin);
+ * t_begin=0,t_count=T gives the reference's full (N,T) output.
+ * Shared-memory mixed-radix FFT (radices 2,3,4,5 and generic primes <= 31); other lengths use
+ * Bluestein.  Supported: T <= 7168 when T factors into primes <= 31, else T <= 2048.
+ * ------------------------------------------------------------------------------------------ */
+size_t leida_hilbert_workspace_bytes(int T);
+int    leida_hilbert_phase_f64(const double* x, int64_t n_series, int T, int64_t x_pitch,
+                               double* phase, int64_t phase_pitch, int t_begin, int t_count,
+                               void* workspace, size_t workspace_bytes, leida_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2a -- phase_coherence       (signal_tools/_signal_tools.py:137-183)
+ * phase: (N, T) with row pitch; dfc: (N, N, T-2) contiguous, t fastest; dFC[i,j,t] =
+ * cos(theta_i(t+1) - theta_j(t+1)).
+ * ------------------------------------------------------------------------------------------ */
+int leida_phase_coherence_f64(const double* phase, int N, int T, int64_t phase_pitch,
+                              double* dfc, leida_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2b -- get_eigenvectors(phase_coherence(.), n=1) without materialising dFC
+ *                                   (signal_tools/_signal_tools.py:137-224)
+ * phase points at the FIRST volume to use of subject 0 / ROI 0; subject s, ROI j, volume v lives
+ * at phase + s*subj_stride + j*row_pitch + v, v in [0, n_vol).  Output row s*n_vol + v:
+ *   lei (fp64, pitch lei_pitch, may be NULL) and xf (fp32, pitch xf_pitch >= N, may be NULL; the
+ *   columns N..xf_pitch-1 are zero-filled -- the layout the k-means kernels want).
+ * Unit 2-norm rows, reference sign rule (:215-220).
+ * ------------------------------------------------------------------------------------------ */
+int leida_eigvec_rank2_f64(const double* phase, int64_t n_subjects, int N, int n_vol,
+                           int64_t subj_stride, int64_t row_pitch,
+                           double* lei, int64_t lei_pitch, float* xf, int64_t xf_pitch,
+                           leida_stream_t stream);
+
+/* Fused stage 1+2 for the Leida pipeline (_leida.py:287-289): x (S, N, T) contiguous fp64 ->
+ * eigenvector rows.  Phases of a chunk of subjects are kept in `workspace` (L2-sized chunks). */
+size_t leida_leading_eigvec_workspace_bytes(int64_t n_subjects, int N, int T);
+int    leida_leading_eigvec_f64(const double* x, int64_t n_subjects, int N, int T,
+                                double* lei, int64_t lei_pitch, float* xf, int64_t xf_pitch,
+                                void* workspace, size_t workspace_bytes, leida_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2b (general path) -- get_eigenvectors(dFC, n=1) for an arbitrary symmetric dFC
+ *                                   (signal_tools/_signal_tools.py:185-224, eigs(...,'LM') at :213)
+ * dfc: (N, N, n_vol) contiguous, t fastest.  Blocked subspace iteration + Rayleigh-Ritz, all
+ * volumes advanced together.  out: (n_vol, N) fp64, unit rows, sign rule applied.
+ * info (device, 4 int32): [0] iterations used, [1] number of volumes not converged to tol, [2..3] scratch.
+ * ------------------------------------------------------------------------------------------ */
+size_t leida_eigvec_dense_workspace_bytes(int N, int n_vol);
+int    leida_eigvec_dense_f64(const double* dfc, int N, int n_vol, double* out, int64_t out_pitch,
+                              double tol, int max_iter, int32_t* info,
+                              void* workspace, size_t workspace_bytes, leida_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 3 -- KMeansLeida.fit        (clustering/_clustering.py:82-153,209-232)
+ *
+ * A "batch" advances many independent runs (K, restart) in lock-step over the same rows.
+ * The caller allocates the arrays; leida_kmeans_layout() says how big they are.
+ *
+ * Row data     X      fp32 (M, x_pitch), x_pitch multiple of 32, columns N..x_pitch-1 zero.
+ *              xnorm  fp64 (M)  row 2-norms  (leida_kmeans_row_norms).
+ * Per run r    K[r] clusters; its centroid rows are crow0[r] .. crow0[r]+K[r]-1 of the pools.
+ * Pools        cent   fp32 (CR, x_pitch)   current centroids
+ *              cnorm  fp64 (CR)            their 2-norms
+ *              acc    int64 (CR, acc_pitch): fixed-point (2^LEIDA_KM_FRAC_BITS) column sums of the
+ *                     member rows in [0,N), member count in column x_pitch   (acc_pitch = x_pitch+8)
+ * Labels       int32 (R, M)   (-1 = unassigned)
+ * Run state    int64 (R, LEIDA_KM_STATE_WORDS): see LEIDA_KM_ST_*
+ *
+ * Everything that is reduced across rows is an int64 sum, so results do not depend on the
+ * order of execution nor on how rows are sharded over GPUs: with G ranks, sum `acc` and the
+ * reducible state words over ranks (ncclAllReduce, sum, int64) between leida_kmeans_assign and
+ * leida_kmeans_update.
+ * ------------------------------------------------------------------------------------------ */
+#define LEIDA_KM_FRAC_BITS     40
+#define LEIDA_KM_STATE_WORDS   8
+#define LEIDA_KM_ST_CHANGED    0   /* rows whose label changed in the last pass     (reducible) */
+#define LEIDA_KM_ST_DIST_HI    1   /* distortion, 2^-40 units                        (reducible) */
+#define LEIDA_KM_ST_DIST_LO    2   /* distortion remainder, 2^-80 units              (reducible) */
+#define LEIDA_KM_ST_RECHECKED  3   /* rows re-evaluated in fp64 in the last pass     (reducible) */
+#define LEIDA_KM_ST_ACTIVE     4   /* 1 while the run is still iterating                          */
+#define LEIDA_KM_ST_PASSES     5   /* assignment passes done (initial pass included)              */
+#define LEIDA_KM_ST_EMPTY      6   /* 1 + index of the first empty cluster seen, 0 = none         */
+#define LEIDA_KM_ST_K          7   /* K of the run (set by leida_kmeans_init)                     */
+
+#define LEIDA_KM_MAX_K         64
+
+int leida_kmeans_row_norms(const float* X, int64_t M, int N, int64_t x_pitch, double* xnorm,
+                           leida_stream_t stream);
+
+/* Pack an arbitrary fp32 (M, N) matrix (pitch src_pitch) into the padded layout above. */
+int leida_kmeans_pack_rows(const float* src, int64_t M, int N, int64_t src_pitch,
+                           float* X, int64_t x_pitch, leida_stream_t stream);
+
+/* Start the runs: centroids of run r = rows init_rows[irow0 .. ] of X_init (clustering/_clustering.py:105-108).
+ * X_init/xi_pitch may be a different array from the rank's shard (multi-GPU: the gathered seed rows);
+ * init_rows (device int64, CR entries) index X_init.  Clears acc, labels := -1, state. */
+int leida_kmeans_init(const float* X_init, int64_t xi_pitch, const int64_t* init_rows,
+                      int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                      float* cent, double* cnorm, int64_t* acc, int32_t* labels, int64_t M,
+                      int64_t* state, leida_stream_t stream);
+
+/* One assignment pass of every ACTIVE run (clustering/_clustering.py:111-114,127-128): label =
+ * argmin_k cosine distance (first minimum), fp32 dot products with an fp64 re-evaluation of every
+ * row whose top-2 margin is inside the fp32 error bound, so labels equal the fp64 argmin.  Rows
+ * whose label changed move their fixed-point contribution between clusters in `acc`.
+ * kmax (host value) = max K over the runs of this call; it selects the register tile, so callers
+ * group runs of similar K.  worklist: device int32 (2*worklist_cap + 8) scratch for the fp64
+ * re-check (rows that do not fit are resolved inline, slower but identical). */
+int leida_kmeans_assign(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
+                        int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
+                        const float* cent, const double* cnorm, int64_t* acc,
+                        int32_t* labels, int64_t* state,
+                        int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
+
+/* Convergence bookkeeping + centroid update of every active run (clustering/_clustering.py:118-133):
+ * a run stops when a pass at Lloyd iteration >= 1 changed no label, or after n_iter iterations;
+ * otherwise its centroids become the member means (:120-125), rounded to fp32.
+ * acc_reduced / state_reduced are the (all-reduced) copies to read; with one GPU pass the same
+ * pointers as acc / state.  An empty cluster stops the run and sets LEIDA_KM_ST_EMPTY. */
+int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                        const int64_t* acc_reduced, const int64_t* state_reduced,
+                        float* cent, double* cnorm, int64_t* state, int n_iter,
+                        int32_t* n_active_out, leida_stream_t stream);
+
+/* Distortion of every run against its final centroids (clustering/_clustering.py:209-232), fp64
+ * per row, accumulated as exact integers into state[DIST_HI/LO]. */
+int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
+                            int n_runs, const int32_t* run_k, const int32_t* run_crow0,
+                            const float* cent, const double* cnorm, const int32_t* labels,
+                            int64_t* state, leida_stream_t stream);
+
+/* Reference-faithful centroid update (validation mode, single GPU): float32 row-after-row sums in
+ * row order and a float32 divide, bit-identical to numpy's y[labels==c].mean(axis=0)
+ * (clustering/_clustering.py:122).  Overwrites cent/cnorm of the runs whose state says active. */
+int leida_kmeans_means_f32_sequential(const float* X, int64_t M, int N, int64_t x_pitch,
+                                      int n_runs, const int32_t* run_k, const int32_t* run_crow0,
+                                      const int32_t* labels, const int64_t* state,
+                                      float* cent, double* cnorm, leida_stream_t stream);
+
+/* KMeansLeida.transform / predict (clustering/_clustering.py:162-207): fp64 cosine distances of
+ * rows to K centroids -> dist (M, K) (may be NULL) and/or labels (M) (may be NULL). */
+int leida_kmeans_transform_f64(const float* X, int64_t M, int N, int64_t x_pitch,
+                               const float* cent, int K, int64_t c_pitch,
+                               double* dist, int32_t* labels, leida_stream_t stream);
+
+/* labels[i] = lut[labels[i]]  (KMeansLeida._remap_labels, clustering/_clustering.py:234-247;
+ * the permutation itself is computed on the host with the reference's numpy calls). */
+int leida_remap_labels_i32(int32_t* labels, int64_t M, const int32_t* lut, int K, leida_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 4 -- dynamics metrics counts
+ *   (dynamics_metrics/_dynamics_metrics.py:131-134 occupancy, :447-453 runs, :242-245 transitions)
+ * labels: int32 (n_cols, M) with pitch label_pitch; column c uses K = col_k[c] states.
+ * Segment g (one (condition, subject) group) = rows seg_rows[seg_off[g] .. seg_off[g+1]) when
+ * seg_rows != NULL, else the contiguous rows [seg_off[g], seg_off[g+1]).
+ * Outputs int32, zero-filled by the call: occ (n_cols, G, kmax), runs (n_cols, G, kmax),
+ * trans (n_cols, G, kmax, kmax).
+ * ------------------------------------------------------------------------------------------ */
+int leida_dynamics_counts_i32(const int32_t* labels, int64_t label_pitch, int n_cols, const int32_t* col_k,
+                              const int64_t* seg_off, const int64_t* seg_rows, int n_segments, int kmax,
+                              int32_t* occ, int32_t* runs, int32_t* trans, leida_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEIDA_B200_H */

@@ -1,0 +1,58 @@
+"""Build libleida_b200.so for sm_100a with nvcc (in-tree, no torch headers needed).
+
+    python leida-python_b200/csrc/build.py [--force] [--verbose]
+
+Output: leida-python_b200/pyleida/_lib/libleida_b200.so (git-ignored; travels to the GPU box).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT_DIR = os.path.join(os.path.dirname(HERE), "pyleida", "_lib")
+OUT = os.path.join(OUT_DIR, "libleida_b200.so")
+SOURCES = ["capi.cu", "signal.cu", "eigdense.cu", "kmeans.cu", "dynamics.cu"]
+HEADERS = [os.path.join(HERE, "common.cuh"), os.path.join(ROOT, "include", "leida_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    obj_dir = os.path.join(HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    objs, procs = [], []
+    for src in SOURCES:
+        s = os.path.join(HERE, src)
+        o = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + HEADERS):
+            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- {src} FAILED ---\n{out}\n")
+        elif verbose or out.strip():
+            sys.stderr.write(f"--- {src} ---\n{out}\n")
+    if failed:
+        raise RuntimeError("nvcc failed")
+    if force or procs or _stale(OUT, objs):
+        cmd = [NVCC, "-shared", "-o", OUT] + objs   # cudart is linked statically (nvcc default)
+        subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

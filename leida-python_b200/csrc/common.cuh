@@ -1,0 +1,57 @@
+// Shared helpers for the LEiDA sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "leida_b200.h"
+
+namespace leida {
+
+void set_error(const char* fmt, ...);
+int  sm_count();
+int  max_smem_optin();
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return LEIDA_ERR_CUDA;
+    }
+    return LEIDA_OK;
+}
+
+#define LEIDA_CUDA_TRY(expr)                                                        \
+    do {                                                                            \
+        cudaError_t e__ = (expr);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            leida::set_error("%s: %s", #expr, cudaGetErrorString(e__));             \
+            return LEIDA_ERR_CUDA;                                                  \
+        }                                                                           \
+    } while (0)
+
+#define LEIDA_REQUIRE(cond, msg)                                                    \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            leida::set_error("invalid argument: %s (%s)", msg, #cond);              \
+            return LEIDA_ERR_INVALID;                                               \
+        }                                                                           \
+    } while (0)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace leida

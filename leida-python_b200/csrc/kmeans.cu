@@ -1,0 +1,708 @@
+// Stage 3 of the LEiDA hot path on sm_100a: cosine k-means, many runs (K, restart) in lock-step.
+// Replaces pyleida/clustering/_clustering.py:82-153 (KMeansLeida.fit), :162-207, :209-232.
+//
+// Design (DESIGN.md section "k-means"):
+//   * assign: one CTA = 128 threads x RPT rows, streams X in 128-byte column chunks through a
+//     cp.async ring (XOR-swizzled so row-per-thread LDS.128 is conflict free), keeps K x RPT fp32
+//     accumulators in registers, centroid chunks are broadcast from shared memory.
+//   * parity: the fp32 score is only trusted when the top-2 margin exceeds a rigorous fp32 error
+//     bound; other rows go to a work list and are re-evaluated in fp64 with the reference's
+//     arithmetic order (scipy cdist 'cosine': sequential dot, dot/(|u||v|), clip, 1-cos, first min).
+//   * centroid sums are int64 fixed point (2^40) and updated incrementally by the rows whose label
+//     changed: exact, order independent, identical for any number of GPUs.
+#include "common.cuh"
+#include <math.h>
+
+namespace leida {
+
+constexpr int kStateWords = LEIDA_KM_STATE_WORDS;
+constexpr double kFracScale = 1099511627776.0;  // 2^40
+
+__device__ __forceinline__ long long quantize(float v) { return __double2ll_rn((double)v * kFracScale); }
+
+__device__ __forceinline__ void atomic_add_ll(long long* p, long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Sequential fp64 dot product in the reference's order (no FMA contraction).
+__device__ __forceinline__ double dot_seq(const float* __restrict__ a, const float* __restrict__ b, int n) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s = __dadd_rn(s, __dmul_rn((double)a[j], (double)b[j]));
+    return s;
+}
+
+__device__ __forceinline__ double cosine_distance(double dot, double na, double nb) {
+    double c = dot / (na * nb);
+    if (fabs(c) > 1.0) c = copysign(1.0, c);
+    return 1.0 - c;
+}
+
+struct AssignParams {
+    const float* X;
+    const double* xnorm;
+    long long M;
+    int N;
+    int XP;  // row pitch of X and cent (floats), multiple of 32
+    const int32_t* run_k;
+    const int32_t* run_crow0;
+    const float* cent;
+    const double* cnorm;
+    long long* acc;
+    int32_t* labels;
+    long long* state;
+    int32_t* worklist;  // [0] = count, entries (run,row) from worklist+8
+    long long worklist_cap;
+    float tau0;
+};
+
+// Move one row's fixed-point contribution between clusters.  Called by `nthreads` cooperating
+// threads (`t` = index of the caller among them).
+__device__ __forceinline__ void move_row(const AssignParams& p, long long row, int crow0, int old_l, int new_l, int t,
+                                         int nthreads) {
+    const float* xr = p.X + row * p.XP;
+    const int AP = p.XP + 8;
+    long long* an = p.acc + (long long)(crow0 + new_l) * AP;
+    long long* ao = p.acc + (long long)(crow0 + (old_l < 0 ? 0 : old_l)) * AP;
+    for (int j = t; j < p.N; j += nthreads) {
+        const long long q = quantize(xr[j]);
+        atomic_add_ll(an + j, q);
+        if (old_l >= 0) atomic_add_ll(ao + j, -q);
+    }
+    if (t == 0) {
+        atomic_add_ll(an + p.XP, 1);
+        if (old_l >= 0) atomic_add_ll(ao + p.XP, -1);
+    }
+}
+
+template <int KP, int RPT>
+__global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
+    constexpr int TR = 128 * RPT;
+    constexpr int STAGES = 3;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float* sx = reinterpret_cast<float*>(smraw);            // [STAGES][TR][32]
+    float* sc = sx + STAGES * TR * 32;                      // [STAGES][KP][32]
+    float* s_cinv = sc + STAGES * KP * 32;                  // [KP]
+    int* s_list = reinterpret_cast<int*>(s_cinv + KP);      // [TR] packed (local row | old<<16 | new<<24)
+    __shared__ int s_nchg;
+
+    const int run = blockIdx.y;
+    if (p.state[(long long)run * kStateWords + LEIDA_KM_ST_ACTIVE] == 0) return;
+    const int K = p.run_k[run];
+    const int crow0 = p.run_crow0[run];
+    const int tid = threadIdx.x;
+    const long long row_base = (long long)blockIdx.x * TR;
+    const int nch = p.XP / 32;
+    const float* cbase = p.cent + (long long)crow0 * p.XP;
+
+    if (tid == 0) s_nchg = 0;
+    if (tid < KP) {
+        float ci = 0.f;
+        if (tid < K) {
+            const double cn = p.cnorm[crow0 + tid];
+            ci = cn > 0.0 ? (float)(1.0 / cn) : 0.f;
+        }
+        s_cinv[tid] = ci;
+    }
+
+    auto issue = [&](int ch, int stage) {
+        float* dx = sx + stage * TR * 32;
+#pragma unroll
+        for (int it = 0; it < RPT * 8; ++it) {
+            const int i = tid + it * 128;
+            const int r = i >> 3, c = i & 7;
+            long long row = row_base + r;
+            const bool ok = row < p.M;
+            if (!ok) row = p.M - 1;
+            cp_async16(dx + r * 32 + ((c ^ (r & 7)) << 2), p.X + row * p.XP + ch * 32 + c * 4, ok);
+        }
+        float* dc = sc + stage * KP * 32;
+        for (int i = tid; i < K * 8; i += 128) {
+            const int r = i >> 3, c = i & 7;
+            cp_async16(dc + r * 32 + c * 4, cbase + (long long)r * p.XP + ch * 32 + c * 4, true);
+        }
+    };
+
+    float acc[RPT][KP];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[i][k] = 0.f;
+
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nch) issue(s, s);
+        cp_async_commit();
+    }
+    const int swz = tid & 7;
+    for (int ch = 0; ch < nch; ++ch) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nxt = ch + STAGES - 1;
+        if (nxt < nch) issue(nxt, nxt % STAGES);
+        cp_async_commit();
+        const float* bx = sx + (ch % STAGES) * TR * 32;
+        const float* bc = sc + (ch % STAGES) * KP * 32;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            float4 xv[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+                xv[i] = *reinterpret_cast<const float4*>(bx + (tid + i * 128) * 32 + ((c4 ^ swz) << 2));
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const float4 cv = *reinterpret_cast<const float4*>(bc + k * 32 + c4 * 4);
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    acc[i][k] = fmaf(xv[i].x, cv.x, acc[i][k]);
+                    acc[i][k] = fmaf(xv[i].y, cv.y, acc[i][k]);
+                    acc[i][k] = fmaf(xv[i].z, cv.z, acc[i][k]);
+                    acc[i][k] = fmaf(xv[i].w, cv.w, acc[i][k]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    int32_t* lab = p.labels + (long long)run * p.M;
+    int n_changed_local = 0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int lr = tid + i * 128;
+        const long long row = row_base + lr;
+        if (row >= p.M) continue;
+        float best = -INFINITY, second = -INFINITY;
+        int bk = 0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            if (k < K) {
+                const float s = acc[i][k] * s_cinv[k];
+                if (s > best) { second = best; best = s; bk = k; }
+                else if (s > second) second = s;
+            }
+        }
+        const float xn = (float)p.xnorm[row];
+        const bool trusted = (best - second) > p.tau0 * xn;
+        if (trusted) {
+            const int old_l = lab[row];
+            if (old_l != bk) {
+                lab[row] = bk;
+                const int slot = atomicAdd(&s_nchg, 1);
+                s_list[slot] = lr | ((old_l & 0xff) << 16) | (bk << 24);
+                ++n_changed_local;
+            }
+        } else {
+            const int slot = atomicAdd(p.worklist, 1);
+            if (slot < p.worklist_cap) {
+                p.worklist[8 + 2 * (long long)slot] = run;
+                p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
+            } else {
+                // work list full: resolve here, serially (slow, correct)
+                const float* xr = p.X + row * p.XP;
+                const double xnd = p.xnorm[row];
+                double bd = INFINITY;
+                int bkk = 0;
+                for (int k = 0; k < K; ++k) {
+                    const double d = cosine_distance(dot_seq(xr, cbase + (long long)k * p.XP, p.N), xnd, p.cnorm[crow0 + k]);
+                    if (d < bd) { bd = d; bkk = k; }
+                }
+                const int old_l = lab[row];
+                if (old_l != bkk) {
+                    lab[row] = bkk;
+                    const int sl = atomicAdd(&s_nchg, 1);
+                    s_list[sl] = lr | ((old_l & 0xff) << 16) | (bkk << 24);
+                    ++n_changed_local;
+                }
+                atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
+            }
+        }
+    }
+    __syncthreads();
+    const int nchg = s_nchg;
+    for (int e = 0; e < nchg; ++e) {
+        const int v = s_list[e];
+        const int lr = v & 0xffff;
+        int old_l = (v >> 16) & 0xff;
+        if (old_l == 0xff) old_l = -1;
+        const int new_l = (v >> 24) & 0xff;
+        move_row(p, row_base + lr, crow0, old_l, new_l, tid, 128);
+    }
+    if (tid == 0 && nchg > 0) atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_CHANGED, nchg);
+}
+
+// fp64 re-evaluation of the rows the fp32 pass could not decide.  One warp per entry.
+__global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    long long count = p.worklist[0];
+    if (count > p.worklist_cap) count = p.worklist_cap;
+    for (long long e = warp; e < count; e += nwarps) {
+        const int run = p.worklist[8 + 2 * e];
+        const long long row = p.worklist[8 + 2 * e + 1];
+        const int K = p.run_k[run];
+        const int crow0 = p.run_crow0[run];
+        const float* xr = p.X + row * p.XP;
+        const double xn = p.xnorm[row];
+        double bd = INFINITY;
+        int bk = 0x7fffffff;
+        for (int k = lane; k < K; k += 32) {
+            const double d = cosine_distance(dot_seq(xr, p.cent + (long long)(crow0 + k) * p.XP, p.N), xn, p.cnorm[crow0 + k]);
+            if (d < bd) { bd = d; bk = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+        }
+        if (bk == 0x7fffffff) bk = 0;   // every distance NaN: numpy's argmin returns the first index
+        int32_t* lab = p.labels + (long long)run * p.M;
+        const int old_l = lab[row];
+        __syncwarp();
+        if (old_l != bk) {
+            if (lane == 0) {
+                lab[row] = bk;
+                atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_CHANGED, 1);
+            }
+            move_row(p, row, crow0, old_l, bk, lane, 32);
+        }
+        if (lane == 0) atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
+    }
+}
+
+__global__ void k_row_norms(const float* __restrict__ X, long long M, int N, long long XP, double* __restrict__ xnorm) {
+    // warp per 32 rows: lanes own rows, sequential fp64 sum of squares (reference order).
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    const float* xr = X + row * XP;
+    double s = 0.0;
+    for (int j = 0; j < N; ++j) {
+        const double v = (double)xr[j];
+        s = __dadd_rn(s, __dmul_rn(v, v));
+    }
+    xnorm[row] = sqrt(s);
+}
+
+__global__ void k_pack_rows(const float* __restrict__ src, long long M, int N, long long sp, float* __restrict__ X,
+                            long long XP) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * XP) return;
+    const long long r = i / XP;
+    const int j = (int)(i - r * XP);
+    X[i] = j < N ? src[r * sp + j] : 0.f;
+}
+
+// One warp per centroid row: 2-norm in fp64 (fixed lane-strided order).
+__device__ __forceinline__ double cent_norm_warp(const float* c, int N, int lane) {
+    double s = 0.0;
+    for (int j = lane; j < N; j += 32) {
+        const double v = (double)c[j];
+        s += v * v;
+    }
+    return sqrt(warp_sum(s));
+}
+
+__global__ void k_init(const float* __restrict__ Xi, long long xi_pitch, const long long* __restrict__ init_rows,
+                       int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int N,
+                       int XP, float* cent, double* cnorm, long long* acc, long long* state) {
+    // one CTA per run
+    const int run = blockIdx.x;
+    const int K = run_k[run], crow0 = run_crow0[run];
+    const int AP = XP + 8;
+    for (int i = threadIdx.x; i < K * XP; i += blockDim.x) {
+        const int k = i / XP, j = i - k * XP;
+        cent[(long long)(crow0 + k) * XP + j] = j < N ? Xi[init_rows[crow0 + k] * xi_pitch + j] : 0.f;
+    }
+    for (int i = threadIdx.x; i < K * AP; i += blockDim.x) acc[(long long)crow0 * AP + i] = 0;
+    if (threadIdx.x < kStateWords) {
+        long long v = 0;
+        if (threadIdx.x == LEIDA_KM_ST_ACTIVE) v = 1;
+        if (threadIdx.x == LEIDA_KM_ST_K) v = K;
+        state[(long long)run * kStateWords + threadIdx.x] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = w; k < K; k += nw) {
+        const double n = cent_norm_warp(cent + (long long)(crow0 + k) * XP, N, lane);
+        if (lane == 0) cnorm[crow0 + k] = n;
+    }
+}
+
+__global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// Control + centroid update, one CTA per run.
+__global__ void __launch_bounds__(256)
+k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int N, int XP,
+         const long long* __restrict__ acc_red, const long long* __restrict__ state_red, float* cent, double* cnorm,
+         long long* state, int n_iter, int32_t* n_active) {
+    const int run = blockIdx.x;
+    long long* st = state + (long long)run * kStateWords;
+    __shared__ int s_go;
+    __shared__ int s_empty;
+    const int K = run_k[run], crow0 = run_crow0[run];
+    const int AP = XP + 8;
+    if (threadIdx.x == 0) {
+        int go = 0;
+        s_empty = 0;
+        if (st[LEIDA_KM_ST_ACTIVE] != 0) {
+            const long long p = st[LEIDA_KM_ST_PASSES];  // index of the pass that just finished
+            st[LEIDA_KM_ST_PASSES] = p + 1;
+            const long long changed = state_red[(long long)run * kStateWords + LEIDA_KM_ST_CHANGED];
+            // pass p >= 1 is Lloyd iteration p-1; the reference tests convergence from iteration 1 on
+            // (clustering/_clustering.py:129-132) and runs at most n_iter iterations (:118).
+            if ((p >= 2 && changed == 0) || p >= n_iter) st[LEIDA_KM_ST_ACTIVE] = 0;
+            else go = 1;
+            if (go) {
+                for (int k = 0; k < K; ++k)
+                    if (acc_red[(long long)(crow0 + k) * AP + XP] <= 0) { s_empty = k + 1; break; }
+                if (s_empty) {
+                    st[LEIDA_KM_ST_EMPTY] = s_empty;
+                    st[LEIDA_KM_ST_ACTIVE] = 0;
+                    go = 0;
+                }
+            }
+            st[LEIDA_KM_ST_CHANGED] = 0;
+            st[LEIDA_KM_ST_RECHECKED] = 0;
+        }
+        s_go = go;
+        if (go) atomicAdd(n_active, 1);
+    }
+    __syncthreads();
+    if (!s_go) return;
+    for (int i = threadIdx.x; i < K * XP; i += blockDim.x) {
+        const int k = i / XP, j = i - k * XP;
+        float v = 0.f;
+        if (j < N) {
+            const long long cnt = acc_red[(long long)(crow0 + k) * AP + XP];
+            const double sum = (double)acc_red[(long long)(crow0 + k) * AP + j] * (1.0 / kFracScale);
+            v = (float)(sum / (double)cnt);
+        }
+        cent[(long long)(crow0 + k) * XP + j] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = w; k < K; k += nw) {
+        const double n = cent_norm_warp(cent + (long long)(crow0 + k) * XP, N, lane);
+        if (lane == 0) cnorm[crow0 + k] = n;
+    }
+}
+
+// Distortion: warp per row, fp64 dot with the assigned centroid, exact integer accumulation.
+__global__ void __launch_bounds__(256)
+k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long long M, int N, int XP,
+             const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, const float* __restrict__ cent,
+             const double* __restrict__ cnorm, const int32_t* __restrict__ labels, long long* state) {
+    const int run = blockIdx.y;
+    const int crow0 = run_crow0[run];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int32_t* lab = labels + (long long)run * M;
+    long long hi = 0, lo = 0;
+    const long long rows_per_cta = 256;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    for (long long row = r0 + w; row < r0 + rows_per_cta && row < M; row += 8) {
+        const int l = lab[row];
+        const float* xr = X + row * XP;
+        const float* cr = cent + (long long)(crow0 + (l < 0 ? 0 : l)) * XP;
+        double s = 0.0;
+        for (int j = lane; j < N; j += 32) s += (double)xr[j] * (double)cr[j];
+        s = warp_sum(s);
+        if (lane == 0) {
+            const double d = cosine_distance(s, xnorm[row], cnorm[crow0 + (l < 0 ? 0 : l)]);
+            const double d2 = d * d * kFracScale;   // exact scaling
+            if (d2 == d2) {
+                const double f = floor(d2);
+                hi += (long long)f;
+                lo += (long long)floor((d2 - f) * kFracScale);
+            } else {
+                hi = (long long)0x4000000000000000LL;   // poison: NaN distance (degenerate row / centroid)
+            }
+        }
+    }
+    __shared__ long long s_hi[8], s_lo[8];
+    if (lane == 0) { s_hi[w] = hi; s_lo[w] = lo; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long a = 0, b = 0;
+        for (int i = 0; i < 8; ++i) { a += s_hi[i]; b += s_lo[i]; }
+        if (a | b) {
+            atomic_add_ll(state + (long long)run * kStateWords + LEIDA_KM_ST_DIST_HI, a);
+            atomic_add_ll(state + (long long)run * kStateWords + LEIDA_KM_ST_DIST_LO, b);
+        }
+    }
+}
+
+__global__ void k_zero_dist(long long* state, int n_runs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_runs) {
+        state[(long long)r * kStateWords + LEIDA_KM_ST_DIST_HI] = 0;
+        state[(long long)r * kStateWords + LEIDA_KM_ST_DIST_LO] = 0;
+    }
+}
+
+// Reference-faithful float32 means: one warp per (run, cluster, 32-column group), rows scanned in
+// order, float32 adds in row order, float32 divide (numpy mean(axis=0) on float32 rows).
+__global__ void __launch_bounds__(128)
+k_means_f32_seq(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ run_k,
+                const int32_t* __restrict__ run_crow0, const int32_t* __restrict__ labels,
+                const long long* __restrict__ state, float* cent, int groups_per_row, int total_rows_dummy) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int run = blockIdx.y;
+    if (state[(long long)run * kStateWords + LEIDA_KM_ST_ACTIVE] == 0) return;
+    const int K = run_k[run], crow0 = run_crow0[run];
+    if (gw >= (long long)K * groups_per_row) return;
+    const int k = (int)(gw / groups_per_row);
+    const int col = (int)(gw % groups_per_row) * 32 + lane;
+    const int32_t* lab = labels + (long long)run * M;
+    float acc = 0.f;
+    long long cnt = 0;
+    bool first = true;
+    for (long long m0 = 0; m0 < M; m0 += 32) {
+        const long long m = m0 + lane;
+        const bool mine = (m < M) && (lab[m] == k);
+        unsigned mask = __ballot_sync(0xffffffffu, mine);
+        cnt += __popc(mask);
+        while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float v = col < XP ? X[(m0 + b) * XP + col] : 0.f;
+            if (first) { acc = v; first = false; }
+            else acc = __fadd_rn(acc, v);
+        }
+    }
+    if (col < XP) {
+        float out = 0.f;
+        if (col < N) out = cnt > 0 ? __fdiv_rn(acc, (float)cnt) : __int_as_float(0x7fc00000);
+        cent[(long long)(crow0 + k) * XP + col] = out;
+    }
+}
+
+__global__ void k_cent_norms(const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0,
+                             const long long* __restrict__ state, const float* __restrict__ cent, int N, int XP,
+                             double* cnorm) {
+    const int run = blockIdx.x;
+    if (state[(long long)run * kStateWords + LEIDA_KM_ST_ACTIVE] == 0) return;
+    const int K = run_k[run], crow0 = run_crow0[run];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = w; k < K; k += nw) {
+        const double n = cent_norm_warp(cent + (long long)(crow0 + k) * XP, N, lane);
+        if (lane == 0) cnorm[crow0 + k] = n;
+    }
+}
+
+// transform / predict: warp per row, fp64.
+__global__ void __launch_bounds__(256)
+k_transform(const float* __restrict__ X, long long M, int N, long long XP, const float* __restrict__ cent, int K,
+            long long CP, double* dist, int32_t* labels) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    const float* xr = X + row * XP;
+    double xx = 0.0;
+    for (int j = lane; j < N; j += 32) xx += (double)xr[j] * (double)xr[j];
+    const double xn = sqrt(warp_sum(xx));
+    double bd = INFINITY;
+    int bk = 0;
+    bool any = false;
+    for (int k = 0; k < K; ++k) {
+        const float* cr = cent + k * CP;
+        double s = 0.0, cc = 0.0;
+        for (int j = lane; j < N; j += 32) {
+            const double c = (double)cr[j];
+            s += (double)xr[j] * c;
+            cc += c * c;
+        }
+        s = warp_sum(s);
+        cc = sqrt(warp_sum(cc));
+        const double d = cosine_distance(s, xn, cc);
+        if (dist && lane == 0) dist[row * K + k] = d;
+        if (d != d && !any) { /* NaN: numpy argmin returns the first NaN */ bd = -INFINITY; bk = k; any = true; }
+        if (d < bd) { bd = d; bk = k; }
+    }
+    if (labels && lane == 0) labels[row] = bk;
+}
+
+__global__ void k_remap(int32_t* labels, long long M, const int32_t* __restrict__ lut, int K) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        const int l = labels[i];
+        if (l >= 0 && l < K) labels[i] = lut[l];
+    }
+}
+
+template <int KP, int RPT>
+static int launch_assign(const AssignParams& p, int n_runs, cudaStream_t st) {
+    constexpr int TR = 128 * RPT;
+    const size_t smem = (size_t)3 * (TR * 32 + KP * 32) * sizeof(float) + KP * sizeof(float) + TR * sizeof(int);
+    LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_assign<KP, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((p.M + TR - 1) / TR), (unsigned)n_runs);
+    k_assign<KP, RPT><<<grid, 128, smem, st>>>(p);
+    return check_launch("k_assign");
+}
+
+}  // namespace leida
+
+using namespace leida;
+
+extern "C" int leida_kmeans_row_norms(const float* X, int64_t M, int N, int64_t x_pitch, double* xnorm,
+                                      leida_stream_t stream) {
+    LEIDA_REQUIRE(X && xnorm, "null pointer");
+    LEIDA_REQUIRE(M >= 0 && N >= 1 && x_pitch >= N, "sizes");
+    if (M == 0) return LEIDA_OK;
+    k_row_norms<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(X, M, N, x_pitch, xnorm);
+    return check_launch("k_row_norms");
+}
+
+extern "C" int leida_kmeans_pack_rows(const float* src, int64_t M, int N, int64_t src_pitch, float* X, int64_t x_pitch,
+                                      leida_stream_t stream) {
+    LEIDA_REQUIRE(src && X, "null pointer");
+    LEIDA_REQUIRE(M >= 0 && N >= 1 && src_pitch >= N && x_pitch >= N, "sizes");
+    if (M == 0) return LEIDA_OK;
+    const long long n = M * x_pitch;
+    k_pack_rows<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, M, N, src_pitch, X, x_pitch);
+    return check_launch("k_pack_rows");
+}
+
+static int check_runs(int n_runs, int N, int64_t x_pitch) {
+    LEIDA_REQUIRE(n_runs >= 1 && n_runs <= 65535, "1 <= n_runs <= 65535 per call");
+    LEIDA_REQUIRE(N >= 1 && x_pitch >= N && x_pitch % 32 == 0, "x_pitch multiple of 32 and >= N");
+    return LEIDA_OK;
+}
+
+extern "C" int leida_kmeans_init(const float* X_init, int64_t xi_pitch, const int64_t* init_rows, int n_runs,
+                                 const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch, float* cent,
+                                 double* cnorm, int64_t* acc, int32_t* labels, int64_t M, int64_t* state,
+                                 leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(X_init && init_rows && run_k && run_crow0 && cent && cnorm && acc && labels && state, "null pointer");
+    int rc = check_runs(n_runs, N, x_pitch);
+    if (rc) return rc;
+    LEIDA_REQUIRE(xi_pitch >= N && M >= 0, "sizes");
+    k_init<<<n_runs, 256, 0, st>>>(X_init, xi_pitch, (const long long*)init_rows, n_runs, run_k, run_crow0, N, (int)x_pitch,
+                                   cent, cnorm, (long long*)acc, (long long*)state);
+    rc = check_launch("k_init");
+    if (rc) return rc;
+    const long long n = (long long)n_runs * M;
+    if (n > 0) {
+        k_fill_i32<<<(unsigned)((n + 1023) / 1024 > 4096 ? 4096 : (n + 1023) / 1024), 256, 0, st>>>(labels, n, -1);
+        rc = check_launch("k_fill_i32");
+    }
+    return rc;
+}
+
+extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
+                                   int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
+                                        const float* cent, const double* cnorm, int64_t* acc, int32_t* labels,
+                                        int64_t* state, int32_t* worklist, int64_t worklist_cap,
+                                        leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && acc && labels && state && worklist, "null pointer");
+    int rc = check_runs(n_runs, N, x_pitch);
+    if (rc) return rc;
+    LEIDA_REQUIRE(kmax >= 2 && kmax <= LEIDA_KM_MAX_K, "2 <= kmax <= 64");
+    LEIDA_REQUIRE(M >= 1 && M < (1LL << 31), "1 <= M < 2^31");
+    LEIDA_REQUIRE(worklist_cap >= 0, "worklist_cap >= 0");
+    AssignParams p;
+    p.X = X; p.xnorm = xnorm; p.M = M; p.N = N; p.XP = (int)x_pitch;
+    p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
+    p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
+    p.worklist = worklist; p.worklist_cap = worklist_cap;
+    // fp32 error bound of score = fl(dot)*fl(1/|c|): (n+2) roundings of relative size 2^-24 on
+    // sum |x_j c_j| <= |x||c|, doubled for the difference of two scores, 10% slack.
+    p.tau0 = 2.2f * (float)(x_pitch + 8) * 5.9604645e-8f;
+    LEIDA_CUDA_TRY(cudaMemsetAsync(worklist, 0, 8 * sizeof(int32_t), st));
+    if (kmax <= 4) rc = launch_assign<4, 2>(p, n_runs, st);
+    else if (kmax <= 8) rc = launch_assign<8, 2>(p, n_runs, st);
+    else if (kmax <= 12) rc = launch_assign<12, 2>(p, n_runs, st);
+    else if (kmax <= 16) rc = launch_assign<16, 2>(p, n_runs, st);
+    else if (kmax <= 20) rc = launch_assign<20, 2>(p, n_runs, st);
+    else if (kmax <= 24) rc = launch_assign<24, 2>(p, n_runs, st);
+    else if (kmax <= 32) rc = launch_assign<32, 2>(p, n_runs, st);
+    else if (kmax <= 40) rc = launch_assign<40, 2>(p, n_runs, st);
+    else if (kmax <= 48) rc = launch_assign<48, 1>(p, n_runs, st);
+    else rc = launch_assign<64, 1>(p, n_runs, st);
+    if (rc) return rc;
+    k_recheck<<<sm_count() * 4, 128, 0, st>>>(p);
+    return check_launch("k_recheck");
+}
+
+extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                                   const int64_t* acc_reduced, const int64_t* state_reduced, float* cent, double* cnorm,
+                                   int64_t* state, int n_iter, int32_t* n_active_out, leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(run_k && run_crow0 && acc_reduced && state_reduced && cent && cnorm && state && n_active_out, "null pointer");
+    int rc = check_runs(n_runs, N, x_pitch);
+    if (rc) return rc;
+    LEIDA_REQUIRE(n_iter >= 0, "n_iter >= 0");
+    LEIDA_CUDA_TRY(cudaMemsetAsync(n_active_out, 0, sizeof(int32_t), st));
+    k_update<<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, (const long long*)acc_reduced,
+                                     (const long long*)state_reduced, cent, cnorm, (long long*)state, n_iter, n_active_out);
+    return check_launch("k_update");
+}
+
+extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch, int n_runs,
+                                       const int32_t* run_k, const int32_t* run_crow0, const float* cent,
+                                       const double* cnorm, const int32_t* labels, int64_t* state,
+                                       leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && labels && state, "null pointer");
+    int rc = check_runs(n_runs, N, x_pitch);
+    if (rc) return rc;
+    k_zero_dist<<<(n_runs + 127) / 128, 128, 0, st>>>((long long*)state, n_runs);
+    if (M > 0) {
+        dim3 grid((unsigned)((M + 255) / 256), (unsigned)n_runs);
+        k_distortion<<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, run_k, run_crow0, cent, cnorm, labels,
+                                           (long long*)state);
+    }
+    return check_launch("k_distortion");
+}
+
+extern "C" int leida_kmeans_means_f32_sequential(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs,
+                                                 const int32_t* run_k, const int32_t* run_crow0, const int32_t* labels,
+                                                 const int64_t* state, float* cent, double* cnorm,
+                                                 leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(X && run_k && run_crow0 && labels && state && cent && cnorm, "null pointer");
+    int rc = check_runs(n_runs, N, x_pitch);
+    if (rc) return rc;
+    const int groups = (int)(x_pitch / 32);
+    const long long warps = (long long)LEIDA_KM_MAX_K * groups;
+    dim3 grid((unsigned)((warps * 32 + 127) / 128), (unsigned)n_runs);
+    k_means_f32_seq<<<grid, 128, 0, st>>>(X, M, N, (int)x_pitch, run_k, run_crow0, labels, (const long long*)state, cent,
+                                          groups, 0);
+    rc = check_launch("k_means_f32_seq");
+    if (rc) return rc;
+    k_cent_norms<<<n_runs, 256, 0, st>>>(run_k, run_crow0, (const long long*)state, cent, N, (int)x_pitch, cnorm);
+    return check_launch("k_cent_norms");
+}
+
+extern "C" int leida_kmeans_transform_f64(const float* X, int64_t M, int N, int64_t x_pitch, const float* cent, int K,
+                                          int64_t c_pitch, double* dist, int32_t* labels, leida_stream_t stream) {
+    LEIDA_REQUIRE(X && cent, "null pointer");
+    LEIDA_REQUIRE(dist || labels, "at least one output");
+    LEIDA_REQUIRE(M >= 0 && N >= 1 && K >= 1 && x_pitch >= N && c_pitch >= N, "sizes");
+    if (M == 0) return LEIDA_OK;
+    const long long threads = M * 32;
+    k_transform<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, M, N, x_pitch, cent, K, c_pitch,
+                                                                                     dist, labels);
+    return check_launch("k_transform");
+}
+
+extern "C" int leida_remap_labels_i32(int32_t* labels, int64_t M, const int32_t* lut, int K, leida_stream_t stream) {
+    LEIDA_REQUIRE(labels && lut, "null pointer");
+    LEIDA_REQUIRE(M >= 0 && K >= 1, "sizes");
+    if (M == 0) return LEIDA_OK;
+    k_remap<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, M, lut, K);
+    return check_launch("k_remap");
+}

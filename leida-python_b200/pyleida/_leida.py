@@ -1,0 +1,226 @@
+"""The Leida pipeline facade over the GPU hot path.
+
+Reference: pyleida/_leida.py:57-401 (class Leida; __init__ :97-109, fit_predict :111-192,
+_execute_all :194-401).  Only the orchestration of the hot path is reproduced:
+phase -> leading eigenvector (:287-289) -> K sweep (:314-321) -> dynamics metrics (:326-331).
+The permutation statistics (:336-342), plots and the results folder are outside the path.
+"""
+import os
+import pickle
+import warnings
+
+import numpy as np
+
+from . import _native as nv
+from .clustering.kmeans import KMeansEngine, identify_states
+from .dynamics_metrics.metrics import Segments, compute_dynamics_metrics
+from .parallel import Comm, row_offsets
+from .signal_tools.phase import leading_eigenvectors, padded_pitch
+
+
+class Bunch(dict):
+    """dict with attribute access (the reference returns sklearn.utils.Bunch objects, _leida.py:377-389)."""
+    __getattr__ = dict.__getitem__
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _load_inputs(data_path):
+    """Minimal loaders for the reference's input folder (data_utils/_data_utils.py:140-268):
+    time_series.pkl or time_series/<subject>/*.csv, metadata.pkl|csv, rois_labels.txt."""
+    import pandas as pd
+    ts_pkl = os.path.join(data_path, "time_series.pkl")
+    if os.path.exists(ts_pkl):
+        with open(ts_pkl, "rb") as f:
+            tseries = pickle.load(f)
+    else:
+        root = os.path.join(data_path, "time_series")
+        tseries = {}
+        for sub in sorted(d for d in os.listdir(root) if os.path.isdir(os.path.join(root, d))):
+            for fn in os.listdir(os.path.join(root, sub)):
+                if fn.endswith(".csv"):
+                    tseries[sub] = np.array(pd.read_csv(os.path.join(root, sub, fn), sep=",", header=None))
+    meta_pkl = os.path.join(data_path, "metadata.pkl")
+    if os.path.exists(meta_pkl):
+        with open(meta_pkl, "rb") as f:
+            classes = pickle.load(f)
+    else:
+        md = pd.read_csv(os.path.join(data_path, "metadata.csv"), sep=",")
+        classes = {s: list(md[md.subject_id == s].condition) for s in np.unique(md.subject_id)}
+    with open(os.path.join(data_path, "rois_labels.txt")) as f:
+        rois = [ln.strip() for ln in f if ln.strip()]
+    return tseries, classes, rois
+
+
+class Leida:
+    """Run the LEiDA pipeline on the GPU.
+
+    Leida(data_path) loads the reference's input folder; Leida.from_arrays(...) takes the same
+    objects already in memory (time_series: dict subject -> (N_ROIs, N_volumes) array; classes:
+    dict subject -> list of condition labels, one per subject or one per volume).
+    """
+
+    def __init__(self, data_path=None, *, time_series=None, classes=None, rois_labels=None, comm=None):
+        if data_path is not None:
+            if not isinstance(data_path, str):
+                raise TypeError("'data_path' must be a string!")
+            if not os.path.exists(data_path):
+                raise ValueError("The specified path could't be founded.")
+            time_series, classes, rois_labels = _load_inputs(data_path)
+        if time_series is None or classes is None:
+            raise ValueError("provide 'data_path' or time_series= and classes=")
+        self.time_series = time_series
+        self.classes = classes
+        n_rois = {np.asarray(v).shape[0] for v in time_series.values()}
+        if len(n_rois) != 1:                                                               # _leida.py:848-851
+            raise Exception("All the subjects must have the same number of ROIs/parcels.")
+        self._N = n_rois.pop()
+        self.rois_labels = list(rois_labels) if rois_labels is not None else [f"ROI_{i + 1}" for i in range(self._N)]
+        if len(self.rois_labels) != self._N:
+            raise Exception("The number of ROIs labels must match the number of rows of the time series.")
+        for s in time_series:
+            if s not in classes:
+                raise Exception(f"subject '{s}' has no condition label in 'classes'")
+        self.rois_coordinates = None
+        self._comm = comm
+
+    @classmethod
+    def from_arrays(cls, time_series, classes, rois_labels=None, comm=None):
+        return cls(None, time_series=time_series, classes=classes, rois_labels=rois_labels, comm=comm)
+
+    # ------------------------------------------------------------------------------------------
+    def fit_predict(self, TR=None, paired_tests=False, n_perm=5_000, save_results=False, random_state=None,
+                    K_min=2, K_max=20, n_init=15, init_indices=None, centroid_update="exact",
+                    keep_eigenvectors=True):
+        """_leida.py:111-192.  K range and n_init are arguments here (the reference hard-codes
+        2..20 and 15, :156-157 / _clustering.py:250); paired_tests / n_perm are validated like the
+        reference but the statistics stage is not run; save_results=True is not supported."""
+        if TR is not None and not isinstance(TR, (int, float)):
+            raise TypeError("'TR' must be 'None', and integer or a floating number!")
+        if not isinstance(paired_tests, bool):
+            raise TypeError("'paired_tests' must be either True or False.")
+        if not isinstance(n_perm, int):
+            raise TypeError("'n_perm' must be an integer!")
+        if n_perm < 100:
+            raise ValueError("The number of permutations cannot be lower than 100.")
+        if not isinstance(save_results, bool):
+            raise TypeError("'save_results' must be a boolean value (True or False)!")
+        if save_results:
+            warnings.warn("save_results=True: the results folder (SURVEY 8f-3) is not written by the GPU path")
+        self._K_min_, self._K_max_ = int(K_min), int(K_max)
+        self._execute_all(TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors)
+        self._is_fitted = True
+        return self
+
+    def _execute_all(self, TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors):
+        torch = nv.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        comm = self._comm if self._comm is not None else Comm()
+        ids = list(self.time_series.keys())
+        N = self._N
+        n_vols = [int(np.asarray(self.time_series[s]).shape[1]) - 2 for s in ids]
+        if min(n_vols) < 1:
+            raise Exception("every subject needs at least 3 volumes")
+        M = int(sum(n_vols))
+        xp = padded_pitch(N)
+        X32 = torch.empty((M, xp), dtype=torch.float32, device=dev)
+        lei64 = torch.empty((M, N), dtype=torch.float64, device=dev) if keep_eigenvectors else None
+        self.h2d_bytes = 0
+        # stage 1+2: consecutive subjects with the same T go through one fused call (_leida.py:279-289)
+        i, row = 0, 0
+        while i < len(ids):
+            T = n_vols[i] + 2
+            j = i
+            while j < len(ids) and n_vols[j] + 2 == T:
+                j += 1
+            host = torch.empty((j - i, N, T), dtype=torch.float64, pin_memory=True)
+            hv = host.numpy()
+            for b, s in enumerate(ids[i:j]):
+                hv[b] = self.time_series[s]
+            x = host.to(dev, non_blocking=True)
+            self.h2d_bytes += host.numel() * 8
+            rows = (j - i) * (T - 2)
+            leading_eigenvectors(x, out_f64=None if lei64 is None else lei64[row:row + rows],
+                                 out_f32=X32[row:row + rows], want_f64=lei64 is not None)
+            row += rows
+            i = j
+        # per-volume metadata (_leida.py:290-297)
+        sub_list = np.repeat(np.asarray(ids, dtype=object), n_vols)
+        per_volume = any(len(self.classes[s]) > 1 for s in ids)
+        if per_volume:
+            cond_list = np.concatenate([
+                np.asarray(self.classes[s], dtype=object)[1:nv_ + 1] if len(self.classes[s]) > 1
+                else np.repeat(np.asarray(self.classes[s][:1], dtype=object), nv_)
+                for s, nv_ in zip(ids, n_vols)])
+            segments = Segments.from_arrays(sub_list.astype(str), cond_list.astype(str))
+            segments.subjects = list(segments.subjects)
+        else:
+            conds = [self.classes[s][0] for s in ids]
+            cond_list = np.repeat(np.asarray(conds, dtype=object), n_vols)
+            segments = Segments.contiguous(np.asarray(ids), np.asarray(conds), n_vols)
+        self._meta = (sub_list, cond_list)
+        # stage 3 (_leida.py:314-321)
+        m_all = comm.all_gather_int(M)
+        off = row_offsets(m_all)
+        engine = KMeansEngine(X32, n_features=N, comm=comm, row_lo=int(off[comm.rank]), m_global=int(off[-1]))
+        import pandas as pd
+        meta = pd.DataFrame({"subject_id": sub_list, "condition": cond_list})
+        predictions, performance, models = identify_states(
+            meta, K_min=self._K_min_, K_max=self._K_max_, n_init=n_init, random_state=random_state, plot=False,
+            init_indices=init_indices, centroid_update=centroid_update, engine=engine)
+        self.kmeans_batch_ = identify_states.last_batch
+        # stage 4 (_leida.py:326-331)
+        Ks = [f"k_{k}" for k in range(self._K_min_, self._K_max_ + 1)]
+        dev_labels = torch.stack([models[k].labels_device_ for k in Ks])
+        dynamics = compute_dynamics_metrics(predictions, TR=TR, _segments=segments, _device_labels=dev_labels)
+        self.predictions = predictions
+        self._lei64 = lei64
+        self._eigenvectors_df = None
+        self._engine = engine
+        self._clustering_ = Bunch(predictions=predictions, performance=performance, models=models)
+        self._dynamics_ = Bunch(dwell_times=dynamics["dwell_times"], occupancies=dynamics["occupancies"],
+                                transitions=dynamics["transitions"], stats=None)
+        self._classes_lst_ = np.unique(cond_list.astype(str)).tolist()
+        self._N_classes_ = len(self._classes_lst_)
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def eigenvectors(self):
+        """DataFrame(subject_id, condition, one column per ROI) like _leida.py:301-303; built on
+        first access from the device copy."""
+        import pandas as pd
+        if getattr(self, "_eigenvectors_df", None) is None:
+            if getattr(self, "_lei64", None) is None:
+                raise Exception("eigenvectors were not kept (keep_eigenvectors=False) or the model is not fitted")
+            df = pd.DataFrame(self._lei64.cpu().numpy(), columns=self.rois_labels)
+            df.insert(0, "subject_id", self._meta[0])
+            df.insert(1, "condition", self._meta[1])
+            self._eigenvectors_df = df
+        return self._eigenvectors_df
+
+    def _check_is_fitted(self):
+        if not hasattr(self, "_is_fitted"):
+            raise Exception("You have to fit the model first by using the 'fit_predict' method.")
+
+    def load_model(self, k=2):
+        self._check_is_fitted()
+        return self._clustering_.models[f"k_{k}"]
+
+    def load_centroids(self, k=2):
+        import pandas as pd
+        self._check_is_fitted()
+        c = self._clustering_.models[f"k_{k}"].cluster_centers_
+        return pd.DataFrame(c.T, columns=[f"PL_state_{i + 1}" for i in range(c.shape[0])], index=self.rois_labels)
+
+    def dwell_times(self, k=2):
+        self._check_is_fitted()
+        return self._dynamics_.dwell_times[f"k_{k}"]
+
+    def occupancies(self, k=2):
+        self._check_is_fitted()
+        return self._dynamics_.occupancies[f"k_{k}"]
+
+    def transitions(self, k=2):
+        self._check_is_fitted()
+        return self._dynamics_.transitions[f"k_{k}"]

@@ -1,0 +1,385 @@
+"""Host side of stage 3: KMeansLeida / identify_states over the CUDA lock-step k-means engine.
+
+Reference: pyleida/clustering/_clustering.py:24-374.  What stays on the host is exactly what the
+reference does with numpy's *global legacy RNG* and tiny arrays: drawing the initial rows
+(:103-105), choosing the best restart (:139-146) and the relabelling permutation (:234-247).
+Everything that touches the (M, N) data runs in libleida_b200.so.
+"""
+import warnings
+
+import numpy as np
+
+from .. import _native as nv
+from ..parallel import Comm, gather_seed_rows
+from ..signal_tools.phase import padded_pitch
+
+_KP_BUCKETS = (4, 8, 12, 16, 20, 24, 32, 40, 48, 64)
+
+
+def _bucket(k):
+    for b in _KP_BUCKETS:
+        if k <= b:
+            return b
+    raise ValueError(f"k must be <= {nv.KM_MAX_K}")
+
+
+class KMeansEngine:
+    """Device-resident rows + lock-step execution of many (K, initial rows) runs.
+
+    X32: CUDA float32 tensor (M_local, pitch), pitch = padded_pitch(N), pad columns zero (the
+    layout leading_eigenvectors() produces), or any (M, N) float array (packed here).
+    comm / row_lo / m_global describe row sharding over ranks (defaults: single GPU).
+    """
+
+    def __init__(self, X, n_features=None, comm=None, row_lo=0, m_global=None):
+        torch = nv.require_cuda()
+        self.torch = torch
+        if isinstance(X, np.ndarray) or not torch.is_tensor(X):
+            X = torch.from_numpy(np.ascontiguousarray(np.asarray(X), dtype=np.float32)).cuda()
+        if not X.is_cuda:
+            X = X.cuda()
+        if X.dim() != 2:
+            raise ValueError("expected a 2D (n_samples, n_features) array")
+        N = int(n_features) if n_features is not None else int(X.shape[1])
+        xp = padded_pitch(N)
+        if X.dtype != torch.float32 or X.shape[1] != xp or not X.is_contiguous():
+            src = X.to(torch.float32).contiguous()
+            packed = torch.empty((src.shape[0], xp), dtype=torch.float32, device=src.device)
+            nv.call("leida_kmeans_pack_rows", nv.ptr(src), src.shape[0], N, src.shape[1], nv.ptr(packed), xp, nv.stream())
+            X = packed
+        self.X, self.N, self.XP = X, N, xp
+        self.M = int(X.shape[0])
+        self.comm = comm if comm is not None else Comm()
+        self.row_lo = int(row_lo)
+        self.m_global = int(m_global) if m_global is not None else self.M
+        self.xnorm = torch.empty(max(self.M, 1), dtype=torch.float64, device=X.device)
+        nv.call("leida_kmeans_row_norms", nv.ptr(X), self.M, N, xp, nv.ptr(self.xnorm), nv.stream())
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1):
+        """runs: list of (k, init_rows) with init_rows = k global row indices.  Returns BatchResult."""
+        torch = self.torch
+        if centroid_update not in ("exact", "reference"):
+            raise ValueError("centroid_update must be 'exact' or 'reference'")
+        if centroid_update == "reference" and self.comm.world > 1:
+            raise ValueError("centroid_update='reference' (sequential float32 sums) cannot be sharded over GPUs")
+        if self.M < 1:
+            raise ValueError("every rank needs at least one row")
+        dev = self.X.device
+        order = sorted(range(len(runs)), key=lambda i: (runs[i][0], i))
+        ks = np.array([runs[i][0] for i in order], dtype=np.int32)
+        if ks.min() < 2 or ks.max() > nv.KM_MAX_K:
+            raise ValueError(f"k must be in [2, {nv.KM_MAX_K}]")
+        crow0 = np.zeros(len(order), dtype=np.int32)
+        crow0[1:] = np.cumsum(ks[:-1])
+        CR = int(ks.sum())
+        R = len(order)
+        seeds_global = np.concatenate([np.asarray(runs[i][1], dtype=np.int64).reshape(-1) for i in order])
+        if seeds_global.size != CR:
+            raise ValueError("each run needs exactly k initial rows")
+        if seeds_global.min() < 0 or seeds_global.max() >= self.m_global:
+            raise ValueError("initial row index out of range")
+
+        run_k = torch.from_numpy(ks).to(dev)
+        run_c0 = torch.from_numpy(crow0).to(dev)
+        AP = self.XP + 8
+        cent = torch.empty((CR, self.XP), dtype=torch.float32, device=dev)
+        cnorm = torch.empty(CR, dtype=torch.float64, device=dev)
+        acc = torch.empty((CR, AP), dtype=torch.int64, device=dev)
+        labels = torch.empty((R, self.M), dtype=torch.int32, device=dev)
+        state = torch.empty((R, nv.STATE_WORDS), dtype=torch.int64, device=dev)
+        cap = int(min(max(self.M // 4, 1 << 16), 1 << 24))
+        worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
+        n_active = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = nv.stream()
+
+        if self.comm.world > 1:
+            seed_rows = gather_seed_rows(self.X, self.N, seeds_global, self.row_lo, self.comm)
+            init_idx = torch.arange(CR, dtype=torch.int64, device=dev)
+            nv.call("leida_kmeans_init", nv.ptr(seed_rows), self.XP, nv.ptr(init_idx), R, nv.ptr(run_k), nv.ptr(run_c0),
+                    self.N, self.XP, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), self.M, nv.ptr(state), st)
+            acc_red = torch.empty_like(acc)
+            state_red = torch.empty_like(state)
+        else:
+            init_idx = torch.from_numpy(seeds_global).to(dev)
+            nv.call("leida_kmeans_init", nv.ptr(self.X), self.XP, nv.ptr(init_idx), R, nv.ptr(run_k), nv.ptr(run_c0),
+                    self.N, self.XP, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), self.M, nv.ptr(state), st)
+            acc_red, state_red = acc, state
+
+        # groups of consecutive (K-sorted) runs sharing a register tile
+        groups, g0 = [], 0
+        for i in range(1, R + 1):
+            if i == R or _bucket(int(ks[i])) != _bucket(int(ks[g0])):
+                groups.append((g0, i, int(ks[g0:i].max())))
+                g0 = i
+        passes = 0
+        launches = 0
+        while True:
+            for (a, b, kmax) in groups:
+                nv.call("leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
+                        run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
+                        labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
+                        nv.ptr(worklist), cap, st)
+                launches += 2
+            if self.comm.world > 1:
+                acc_red.copy_(acc)
+                state_red.copy_(state)
+                self.comm.all_reduce_sum_(acc_red)
+                self.comm.all_reduce_sum_(state_red)
+            nv.call("leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
+                    nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active), st)
+            launches += 1
+            if centroid_update == "reference":
+                nv.call("leida_kmeans_means_f32_sequential", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_k),
+                        nv.ptr(run_c0), nv.ptr(labels), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm), st)
+                launches += 2
+            passes += 1
+            if passes % poll_every == 0 or passes > n_iter:
+                if int(n_active.item()) == 0:
+                    break
+            if passes > n_iter + 2:
+                raise nv.LeidaCudaError("k-means did not terminate (internal error)")
+        nv.call("leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
+                nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), st)
+        launches += 2
+        if self.comm.world > 1:
+            state_red.copy_(state)
+            self.comm.all_reduce_sum_(state_red)
+            acc_red.copy_(acc)
+            self.comm.all_reduce_sum_(acc_red)
+            dist_words = state_red[:, [nv.ST_DIST_HI, nv.ST_DIST_LO]].cpu().numpy()
+        else:
+            dist_words = state[:, [nv.ST_DIST_HI, nv.ST_DIST_LO]].cpu().numpy()
+        st_host = state.cpu().numpy()
+        counts = acc_red[:, self.XP].cpu().numpy()
+        hi = dist_words[:, 0].astype(np.float64)
+        lo = dist_words[:, 1].astype(np.float64)
+        inertia = hi * 2.0 ** -40 + lo * 2.0 ** -80
+        inertia[dist_words[:, 0] >= (1 << 62)] = np.nan
+        empty = st_host[:, nv.ST_EMPTY].copy()
+        inertia[empty > 0] = np.nan
+        inv = np.empty(R, dtype=np.int64)
+        inv[np.asarray(order)] = np.arange(R)
+        return BatchResult(self, inv, ks, crow0, cent, labels, inertia, st_host[:, nv.ST_PASSES].copy(), empty, counts,
+                           launches, passes)
+
+    def predict(self, centers):
+        """argmin cosine distance to `centers` (K, N) for every local row -> CUDA int32 (M,)."""
+        torch = self.torch
+        c = torch.as_tensor(np.ascontiguousarray(centers, dtype=np.float32)).to(self.X.device)
+        out = torch.empty(self.M, dtype=torch.int32, device=self.X.device)
+        nv.call("leida_kmeans_transform_f64", nv.ptr(self.X), self.M, self.N, self.XP, nv.ptr(c), c.shape[0], c.shape[1],
+                None, nv.ptr(out), nv.stream())
+        return out
+
+
+class BatchResult:
+    """Results of KMeansEngine.run, indexed by the caller's run order."""
+
+    def __init__(self, engine, inv, ks, crow0, cent, labels, inertia, passes, empty, counts, launches, lockstep_passes):
+        self.engine, self._inv = engine, inv
+        self._ks, self._crow0, self._cent, self._labels = ks, crow0, cent, labels
+        self._inertia, self._passes, self._empty, self._counts = inertia, passes, empty, counts
+        self.launches = launches
+        self.lockstep_passes = lockstep_passes
+
+    def k(self, i): return int(self._ks[self._inv[i]])
+    def inertia(self, i): return float(self._inertia[self._inv[i]])
+    def passes(self, i): return int(self._passes[self._inv[i]])
+    def empty_cluster(self, i): return int(self._empty[self._inv[i]])
+
+    def total_passes(self):
+        return int(self._passes.sum())
+
+    def counts(self, i):
+        j = self._inv[i]
+        return self._counts[self._crow0[j]:self._crow0[j] + self._ks[j]].astype(np.int64)
+
+    def centers_device(self, i):
+        j = self._inv[i]
+        return self._cent[int(self._crow0[j]):int(self._crow0[j] + self._ks[j]), :self.engine.N]
+
+    def labels_device(self, i):
+        return self._labels[int(self._inv[i])]
+
+
+def _remap_permutation(counts):
+    """KMeansLeida._remap_labels (clustering/_clustering.py:234-247) from the cluster sizes.
+
+    Returns (lut, order): new_label = lut[old_label]; centers_new = centers[order].  Uses the same
+    numpy calls as the reference so ties between equally populated clusters resolve identically.
+    """
+    counts = np.asarray(counts, dtype=np.int64)
+    label = np.nonzero(counts)[0]                     # np.unique(labels_) of :242
+    freq = counts[label]                              # its return_counts
+    sorted_idxs = np.argsort(freq)[::-1]              # :243
+    if len(label) != len(counts):
+        # The reference indexes the *unique* list by position (:244-247) and breaks when a cluster
+        # is empty; here: populated clusters by descending size, empty ones last.
+        warnings.warn("a cluster ended empty; relabelling by descending size with empty clusters last")
+        order = np.concatenate([label[sorted_idxs], np.nonzero(counts == 0)[0]])
+        lut = np.empty(len(counts), dtype=np.int32)
+        lut[order] = np.arange(len(counts), dtype=np.int32)
+        return lut, order
+    lut = np.empty(len(counts), dtype=np.int32)
+    lut[sorted_idxs] = label.astype(np.int32)         # dct = {sorted_idxs[i]: label[i]}  (:244)
+    return lut, sorted_idxs
+
+
+def _select_best(inertias):
+    """Restart selection of clustering/_clustering.py:139-146: first run, replaced only by a
+    strictly smaller distortion.  Deviation: runs that hit an empty cluster (inertia NaN -- the
+    reference would carry NaN centroids) are skipped with a warning instead of winning by default."""
+    best = None
+    for i, d in enumerate(inertias):
+        if np.isnan(d):
+            continue
+        if best is None or d < inertias[best]:
+            best = i
+    if best is None:
+        raise RuntimeError("every k-means restart ended with an empty cluster")
+    if any(np.isnan(d) for d in inertias):
+        warnings.warn("some k-means restarts hit an empty cluster and were discarded")
+    return best
+
+
+def _draw_inits(M, k, n_init, random_state):
+    """Initial rows exactly as the reference draws them (clustering/_clustering.py:101-105):
+    re-seeding before every restart when random_state is an int (=> identical restarts)."""
+    out = []
+    for _ in range(n_init):
+        if random_state is not None:
+            np.random.seed(random_state)
+        out.append(np.random.choice(M, k, replace=False))
+    return out
+
+
+def _dedupe(inits):
+    """Index of the first identical earlier restart for each restart (bit-identical runs)."""
+    seen, first = {}, []
+    for i, idx in enumerate(inits):
+        key = np.asarray(idx, dtype=np.int64).tobytes()
+        first.append(seen.setdefault(key, i))
+    return first
+
+
+class KMeansLeida:
+    """K-Means with cosine distance on the GPU; same surface as the reference class
+    (clustering/_clustering.py:24-247): KMeansLeida(k, metric, n_init, n_iter), fit(y, random_state),
+    predict, transform, cluster_centers_, labels_, inertia_.
+
+    Extra keyword arguments of fit(): init_indices (list of n_init index arrays, bypasses the
+    legacy-RNG draw), centroid_update ('exact' | 'reference'), engine (reuse device
+    data).  metric='euclidean' is accepted by the constructor like the reference but only the
+    cosine path named by the north star is implemented.
+    """
+
+    def __init__(self, k=2, metric="cosine", n_init=10, n_iter=1_000):
+        if not isinstance(metric, str):
+            raise TypeError("'metric' must be a string!")
+        if metric not in ["euclidean", "cosine"]:
+            raise ValueError("'metric' must be either 'cosine' or 'euclidean'")
+        for name, val in {"k": k, "n_init": n_init, "n_iter": n_iter}.items():
+            if not isinstance(val, int):
+                raise TypeError(f"'{name}' must be an integer")
+        if k < 2:
+            raise ValueError("'k' must be > 1")
+        self._k_, self._metric_, self._n_iter_, self._n_init_ = k, metric, n_iter, n_init
+
+    def fit(self, y, random_state=None, init_indices=None, centroid_update="exact", engine=None):
+        if self._metric_ != "cosine":
+            raise NotImplementedError("only metric='cosine' runs on the GPU path")
+        eng = engine if engine is not None else KMeansEngine(y)
+        M = eng.m_global
+        inits = list(init_indices) if init_indices is not None else _draw_inits(M, self._k_, self._n_init_, random_state)
+        if len(inits) != self._n_init_:
+            raise ValueError("init_indices must hold n_init index arrays")
+        first = _dedupe(inits)
+        uniq = sorted(set(first))
+        res = eng.run([(self._k_, inits[i]) for i in uniq], n_iter=self._n_iter_, centroid_update=centroid_update)
+        self._finish(eng, res, [uniq.index(f) for f in first])
+        return self
+
+    def _finish(self, eng, res, run_of_init):
+        inertias = [res.inertia(r) for r in run_of_init]
+        best_init = _select_best(inertias)
+        r = run_of_init[best_init]
+        lut, order = _remap_permutation(res.counts(r))
+        torch = eng.torch
+        lab = res.labels_device(r).clone()
+        lut_d = torch.from_numpy(lut).to(lab.device)
+        nv.call("leida_remap_labels_i32", nv.ptr(lab), lab.numel(), nv.ptr(lut_d), len(lut), nv.stream())
+        self.labels_device_ = lab
+        self.labels_ = lab.cpu().numpy().astype(np.int64)
+        self.cluster_centers_ = res.centers_device(r).cpu().numpy()[order, :]
+        self.inertia_ = np.float64(inertias[best_init])
+        self.n_passes_ = res.passes(r)
+        self.inertia_runs_ = inertias
+        self.best_init_ = best_init
+        self._is_fitted = True
+
+    def _check_is_fitted(self):
+        if not hasattr(self, "_is_fitted"):
+            raise Exception("You have to fit the model first by using the 'fit' method.")
+
+    def transform(self, y, closest=False):
+        """Cosine distances to the centroids, fp64 (clustering/_clustering.py:162-187)."""
+        self._check_is_fitted()
+        torch = nv.require_cuda()
+        eng = y if isinstance(y, KMeansEngine) else KMeansEngine(y, n_features=self.cluster_centers_.shape[1])
+        c = torch.from_numpy(np.ascontiguousarray(self.cluster_centers_, dtype=np.float32)).to(eng.X.device)
+        d = torch.empty((eng.M, c.shape[0]), dtype=torch.float64, device=eng.X.device)
+        nv.call("leida_kmeans_transform_f64", nv.ptr(eng.X), eng.M, eng.N, eng.XP, nv.ptr(c), c.shape[0], c.shape[1],
+                nv.ptr(d), None, nv.stream())
+        d = d.cpu().numpy()
+        return d.min(1) if closest else d
+
+    def predict(self, y):
+        """Closest centroid of each row (clustering/_clustering.py:189-207)."""
+        self._check_is_fitted()
+        eng = y if isinstance(y, KMeansEngine) else KMeansEngine(y, n_features=self.cluster_centers_.shape[1])
+        return eng.predict(self.cluster_centers_).cpu().numpy().astype(np.int64)
+
+
+def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=None, plot=True, save_results=False,
+                    path=None, init_indices=None, centroid_update="exact", engine=None, scores=False):
+    """K sweep of clustering/_clustering.py:250-374 with every (K, restart) run advanced in
+    lock-step on the GPU.  Returns (predictions, clustering_performance, models) like the reference.
+
+    eigens_dataset: DataFrame with 'subject_id', 'condition' and one column per ROI (the reference's
+    input), or a (metadata DataFrame, KMeansEngine) pair through `engine` to reuse device data.
+    The Dunn / silhouette / Davies-Bouldin columns (:331-339) are outside the accelerated path
+     and are reported as NaN; `plot` is accepted and ignored (no plotting stack).
+    init_indices: optional {k: [idx_r ...]} replacing the legacy-RNG draws.
+    """
+    import pandas as pd
+    if save_results:
+        raise NotImplementedError("results I/O (SURVEY 8f-3) is not part of the accelerated path")
+    meta = eigens_dataset[["subject_id", "condition"]].copy()
+    if engine is None:
+        X = np.array(eigens_dataset.iloc[:, 2:], dtype=np.float32)            # :316
+        engine = KMeansEngine(X)
+    M = engine.m_global
+    if M > 30_000 and init_indices is None:
+        # :318-320 -- the reference draws its score sub-sample here; repeating the draw keeps the
+        # global RNG stream (and therefore every later initial centroid) aligned with it.
+        np.random.choice(np.arange(M), size=30_000, replace=False)
+    runs, plan = [], {}
+    for k in range(K_min, K_max + 1):                                          # :326
+        inits = list(init_indices[k]) if init_indices is not None else _draw_inits(M, k, n_init, random_state)
+        first = _dedupe(inits)
+        uniq = sorted(set(first))
+        base = len(runs)
+        runs.extend((k, inits[i]) for i in uniq)
+        plan[k] = [base + uniq.index(f) for f in first]
+    res = engine.run(runs, n_iter=1_000, centroid_update=centroid_update)
+    models, perf = {}, []
+    for k in range(K_min, K_max + 1):
+        km = KMeansLeida(k=k, n_init=n_init, n_iter=1_000)
+        km._finish(engine, res, plan[k])
+        models[f"k_{k}"] = km
+        perf.append({"k": k, "Dunn_score": np.nan, "distortion": km.inertia_, "silhouette_score": np.nan,
+                     "Davies-Bouldin_score": np.nan})
+        meta[f"k_{k}"] = km.labels_                                            # :342
+    identify_states.last_batch = res
+    return meta, pd.DataFrame(perf), models

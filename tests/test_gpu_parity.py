@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the pyleida host layer) against the
+committed golden fixtures (unmodified reference outputs) and against the CPU oracle on seeded
+inputs.  Tolerances follow BASELINE.json's north_star / SURVEY 8d:
+  phases: wrapped angular error <= 1e-5*pi;  eigenvectors: max|v - v_ref| <= 1e-5 * max|v_ref| per row;
+  labels: identical after _remap_labels;  inertia: rel 1e-6;  metric tables: bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pyleida
+    return pyleida
+
+
+@pytest.fixture(scope="module")
+def O():
+    import leida_oracle
+    return leida_oracle
+
+
+@pytest.fixture(scope="module")
+def sig():
+    return np.load(os.path.join(GOLD, "signal_cases.npz"))
+
+
+def wrapped(a, b):
+    return np.abs(np.angle(np.exp(1j * (a - b))))
+
+
+def eig_ok(got, ref):
+    return np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref).max(axis=1, keepdims=True))
+
+
+# ---- stage 1 --------------------------------------------------------------------------------
+def test_hilbert_phase_golden(P, sig):
+    for i in range(int(sig["n_cases"])):
+        got = P.signal_tools.hilbert_phase(sig[f"x_{i}"])
+        assert got.shape == sig[f"phase_{i}"].shape and got.dtype == np.float64
+        err = wrapped(got, sig[f"phase_{i}"]).max()
+        assert err <= 1e-5 * np.pi, (i, err)
+        assert err <= 1e-10, (i, err)
+
+
+@pytest.mark.parametrize("T", [3, 4, 5, 7, 16, 50, 59, 77, 128, 200, 211, 1200, 1201, 2000, 2047, 4096])
+def test_hilbert_phase_lengths_vs_oracle(P, O, T):
+    rng = np.random.default_rng(T)
+    x = rng.standard_normal((5, T))
+    got = P.signal_tools.hilbert_phase(x)
+    assert wrapped(got, O.hilbert_phase(x)).max() <= 1e-9
+
+
+def test_hilbert_pure_tone_is_a_ramp(P):
+    T = 400
+    t = np.arange(T)
+    x = np.cos(2 * np.pi * 8 * t / T)[None, :].repeat(3, 0)
+    ph = P.signal_tools.hilbert_phase(x)
+    assert wrapped(ph[0], 2 * np.pi * 8 * t / T).max() < 1e-9
+
+
+def test_hilbert_unsupported_length_raises(P):
+    from pyleida._native import LeidaCudaError
+    with pytest.raises(LeidaCudaError):
+        P.signal_tools.hilbert_phase(np.zeros((2, 2053 * 2)))     # prime factor > 31 and > 2048
+
+
+# ---- stage 2 --------------------------------------------------------------------------------
+def test_phase_coherence_golden(P, sig):
+    for i in range(int(sig["n_cases"])):
+        if f"dfc_{i}" in sig:
+            got = P.signal_tools.phase_coherence(sig[f"phase_{i}"])
+            np.testing.assert_allclose(got, sig[f"dfc_{i}"], atol=1e-14)
+    with pytest.raises(Exception):
+        P.signal_tools.phase_coherence(np.zeros(5))
+
+
+def test_rank2_eigenvectors_golden(P, sig):
+    for i in range(int(sig["n_cases"])):
+        got = P.signal_tools.eigenvectors_from_phases(sig[f"phase_{i}"])
+        assert eig_ok(got, sig[f"lei_{i}"]), i
+        assert np.abs(got - sig[f"lei_{i}"]).max() < 1e-12
+    got = P.signal_tools.eigenvectors_from_phases(sig["tie_phase"])
+    np.testing.assert_allclose(got, sig["tie_lei"], atol=1e-13)
+
+
+def test_fused_leading_eigenvectors_golden(P, sig):
+    for i in range(int(sig["n_cases"])):
+        lei, xf = P.signal_tools.leading_eigenvectors(sig[f"x_{i}"][None])
+        assert eig_ok(lei, sig[f"lei_{i}"]), i
+        x32 = xf.cpu().numpy()
+        n = sig[f"x_{i}"].shape[0]
+        assert np.all(x32[:, n:] == 0)
+        np.testing.assert_allclose(x32[:, :n], sig[f"lei_{i}"].astype(np.float32), atol=2e-7)
+
+
+def test_dense_eigenvectors_golden_and_generic(P, O, sig):
+    for i in range(int(sig["n_cases"])):
+        dfc = O.phase_coherence(sig[f"phase_{i}"])
+        got, info = P.signal_tools.get_eigenvectors(dfc, return_info=True)
+        assert info["unconverged"] == 0, info
+        assert eig_ok(got, sig[f"lei_{i}"]), i
+    # generic symmetric matrices with a clear leading eigenvalue (not rank 2)
+    rng = np.random.default_rng(2)
+    N, T = 24, 40
+    A = rng.standard_normal((N, N, T))
+    A = A + A.transpose(1, 0, 2)
+    u = rng.standard_normal((N, T))
+    A += 6.0 * u[:, None, :] * u[None, :, :] / N
+    got, info = P.signal_tools.get_eigenvectors(A, max_iter=400, return_info=True)
+    assert info["unconverged"] == 0, info
+    ref = O.get_eigenvectors(A)
+    assert np.abs(got - ref).max() < 1e-8
+    with pytest.raises(Exception):
+        P.signal_tools.get_eigenvectors(np.zeros((3, 3)))
+
+
+# ---- stage 3 --------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["exact", "reference"])
+def test_kmeans_golden(P, mode):
+    g = np.load(os.path.join(GOLD, "kmeans_cases.npz"))
+    for c in range(int(g["n_cases"])):
+        k, n_init, seed, is_int = (int(v) for v in g[f"case{c}_meta"])
+        X = g["X_" + str(g[f"case{c}_data"])]
+        km = P.clustering.KMeansLeida(k=k, n_init=n_init)
+        if is_int:
+            km.fit(X, random_state=seed, centroid_update=mode)
+        else:
+            np.random.seed(seed)
+            km.fit(X, random_state=None, centroid_update=mode)
+        assert km.labels_.dtype == np.int64
+        assert np.array_equal(km.labels_, g[f"case{c}_labels"]), (c, mode)
+        assert km.inertia_ == pytest.approx(float(g[f"case{c}_inertia"]), rel=1e-6)
+        if mode == "reference":
+            assert np.array_equal(km.cluster_centers_, g[f"case{c}_centers"]), c        # bit-identical float32 means
+        else:
+            np.testing.assert_allclose(km.cluster_centers_, g[f"case{c}_centers"], rtol=0, atol=5e-7)
+
+
+def test_kmeans_predict_transform(P, O):
+    g = np.load(os.path.join(GOLD, "kmeans_cases.npz"))
+    X = g["X_states"]
+    km = P.clustering.KMeansLeida(k=5, n_init=1)
+    km.fit(X, random_state=3)
+    ref = O.KMeansLeida(k=5, n_init=1)
+    ref.cluster_centers_, ref._is_fitted = km.cluster_centers_, True
+    np.testing.assert_allclose(km.transform(X), ref.transform(X), atol=1e-14)
+    assert np.array_equal(km.predict(X), ref.predict(X))
+    assert np.array_equal(km.predict(X), km.labels_)
+    np.testing.assert_allclose(km.transform(X, closest=True), ref.transform(X, closest=True), atol=1e-14)
+
+
+def test_kmeans_constructor_errors(P):
+    K = P.clustering.KMeansLeida
+    with pytest.raises(TypeError):
+        K(metric=3)
+    with pytest.raises(ValueError):
+        K(metric="manhattan")
+    with pytest.raises(TypeError):
+        K(k=2.0)
+    with pytest.raises(ValueError):
+        K(k=1)
+    with pytest.raises(Exception):
+        K(k=2).predict(np.zeros((3, 3), dtype=np.float32))
+
+
+@pytest.mark.parametrize("kind,N,S,T", [("states", 90, 20, 200), ("iid", 33, 6, 150)])
+def test_kmeans_vs_oracle_config1(P, O, kind, N, S, T):
+    """Config-1-sized sweep (20 x 90 x 200) against the oracle with shared explicit initial rows."""
+    from pyleida import synthetic
+    ts, _ = synthetic.make_dataset(S, N, T, kind)
+    lei = np.vstack([O.leading_eigvec_rank2(O.hilbert_phase(v)) for v in ts.values()])
+    X = lei.astype(np.float32)
+    inits = synthetic.init_indices(X.shape[0], 2, 9, 2, seed=4)
+    eng = P.clustering.KMeansEngine(X)
+    for k in (2, 3, 5, 9):
+        ref = O.KMeansLeida(k=k, n_init=2).fit(X, init_indices=inits[k])
+        for mode in ("exact", "reference"):
+            km = P.clustering.KMeansLeida(k=k, n_init=2).fit(X, init_indices=inits[k], centroid_update=mode, engine=eng)
+            assert np.array_equal(km.labels_, ref.labels_), (k, mode)
+            assert km.inertia_ == pytest.approx(ref.inertia_, rel=1e-9)
+            assert km.n_passes_ == ref.n_iter_runs_[km.best_init_] + 1
+            if mode == "reference":
+                assert np.array_equal(km.cluster_centers_, ref.cluster_centers_)
+
+
+def test_kmeans_large_k_and_wide_rows(P, O):
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((3000, 400)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    for k in (24, 40, 64):
+        idx = [rng.choice(3000, k, replace=False)]
+        ref = O.KMeansLeida(k=k, n_init=1, n_iter=6).fit(X, init_indices=idx)
+        km = P.clustering.KMeansLeida(k=k, n_init=1, n_iter=6).fit(X, init_indices=idx, centroid_update="reference")
+        assert np.array_equal(km.labels_, ref.labels_), k
+        assert km.inertia_ == pytest.approx(ref.inertia_, rel=1e-9)
+
+
+def test_kmeans_properties_large(P):
+    """Size-independent properties at a size the oracle cannot reach in seconds."""
+    import torch
+    rng = np.random.default_rng(0)
+    M, N, K = 200_000, 116, 7
+    cent = rng.standard_normal((K, N))
+    X = (cent[rng.integers(0, K, M)] + 0.8 * rng.standard_normal((M, N))).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    eng = P.clustering.KMeansEngine(X)
+    idx = [rng.choice(M, K, replace=False)]
+    a = P.clustering.KMeansLeida(k=K, n_init=1).fit(None, init_indices=idx, engine=eng)
+    b = P.clustering.KMeansLeida(k=K, n_init=1).fit(None, init_indices=idx, engine=eng)
+    assert np.array_equal(a.labels_, b.labels_) and a.inertia_ == b.inertia_            # run-to-run deterministic
+    # fixed point: labels are the argmin of the final centroids, centroids are the member means
+    assert np.array_equal(a.predict(eng), a.labels_)
+    means = np.vstack([X[a.labels_ == c].astype(np.float64).mean(0) for c in range(K)])
+    np.testing.assert_allclose(a.cluster_centers_, means, atol=1e-6)
+    # relabelling: sizes are non-increasing, and permuting the initial rows only permutes clusters
+    sizes = np.bincount(a.labels_, minlength=K)
+    assert np.all(np.diff(sizes) <= 0)
+    c = P.clustering.KMeansLeida(k=K, n_init=1).fit(None, init_indices=[idx[0][::-1].copy()], engine=eng)
+    assert np.array_equal(c.labels_, a.labels_) and c.inertia_ == a.inertia_
+    # inertia equals the fp64 sum of squared cosine distances to the assigned centroid
+    Xd = X.astype(np.float64)
+    C = a.cluster_centers_.astype(np.float64)[a.labels_]
+    d = 1 - (Xd * C).sum(1) / (np.linalg.norm(Xd, axis=1) * np.linalg.norm(C, axis=1))
+    assert a.inertia_ == pytest.approx((d ** 2).sum(), rel=1e-10)
+    torch.cuda.synchronize()
+
+
+# ---- stage 4 --------------------------------------------------------------------------------
+def test_single_sequence_metrics_golden(P):
+    g = np.load(os.path.join(GOLD, "metric_cases.npz"))
+    D = P.dynamics_metrics
+    for i in range(int(g["n_cases"])):
+        lab, k = g[f"labels_{i}"], int(g[f"k_{i}"])
+        occ = D.fractional_occupancy(lab)
+        dense = np.zeros(k)
+        dense[occ.cluster.values] = occ.occupancy.values
+        assert np.array_equal(dense, g[f"occ_{i}"])
+        for tr, key in ((0.72, "dwell_tr"), (None, "dwell")):
+            _, dw = D.dwell_times(lab, TR=tr)
+            dense = np.zeros(k)
+            dense[dw.Cluster.values] = dw.Mean_lifetime.values
+            assert np.array_equal(dense, g[f"{key}_{i}"])
+        assert np.array_equal(D.transition_probabilities(lab, k), g[f"trans_{i}"])
+        assert np.array_equal(D.transition_probabilities(lab, k, norm=False), g[f"trans_raw_{i}"])
+
+
+def test_group_metrics_noncontiguous_segments(P, O):
+    import pandas as pd
+    rng = np.random.default_rng(9)
+    subs = np.repeat([f"s{i}" for i in range(5)], 30)
+    conds = np.tile(np.repeat(["B", "A", "B"], 10), 5)            # per-volume conditions: groups interleave
+    lab = np.repeat(rng.integers(0, 4, size=75), 2)
+    meta = pd.DataFrame({"subject_id": subs, "condition": conds})
+    t = O.dynamics_tables(subs, conds, lab, TR=2.0)
+    D = P.dynamics_metrics
+    occ = D.fractional_occupancy_group(meta, lab)
+    assert list(zip(occ.subject_id, occ.condition)) == t["rows"]
+    assert np.array_equal(occ.iloc[:, 2:].values, t["occupancies"])
+    assert np.array_equal(D.dwell_times_group(meta, lab, TR=2.0).iloc[:, 2:].values, t["dwell_times"])
+    assert np.array_equal(D.transition_probabilities_group(meta, lab).iloc[:, 2:].values, t["transitions"])
+    with pytest.raises(AssertionError):
+        D.fractional_occupancy_group(meta, lab[:-1])
+
+
+# ---- pipeline -------------------------------------------------------------------------------
+def test_pipeline_golden(P):
+    from pyleida import synthetic
+    g = np.load(os.path.join(GOLD, "pipeline_case.npz"))
+    S, N, T = int(g["S"]), int(g["N"]), int(g["T"])
+    ts, classes = synthetic.make_dataset(S, N, T, "states")
+    for mode in ("exact", "reference"):
+        m = P.Leida.from_arrays(ts, classes).fit_predict(TR=0.72, random_state=0, K_min=2, K_max=6, n_init=3,
+                                                         centroid_update=mode)
+        lei = m.eigenvectors.iloc[:, 2:].values
+        assert eig_ok(lei, g["lei"])
+        assert list(m.eigenvectors.subject_id) == list(g["subject_id"])
+        for k in range(2, 7):
+            assert np.array_equal(m.predictions[f"k_{k}"].values, g[f"labels_k{k}"]), (k, mode)
+            assert m.load_model(k).inertia_ == pytest.approx(float(g[f"inertia_k{k}"]), rel=1e-6)
+            for name in ("occupancies", "dwell_times", "transitions"):
+                tab = getattr(m._dynamics_, name)[f"k_{k}"]
+                assert np.array_equal(tab.iloc[:, 2:].values, g[f"{name}_k{k}"]), (k, name)
+                assert list(tab.columns[2:]) == list(g[f"{name}_k{k}_cols"])
+                assert list(tab.subject_id) == list(g[f"{name}_k{k}_subject"])
+                assert list(tab.condition) == list(g[f"{name}_k{k}_condition"])
+
+
+def test_pipeline_ragged_and_per_volume_conditions(P, O):
+    from pyleida import synthetic
+    ts = {f"s{i}": synthetic.subject_series(i, 10, T) for i, T in enumerate([40, 40, 55, 31, 31])}
+    classes = {"s0": ["A"], "s1": ["B"], "s2": ["A"], "s3": ["B"], "s4": ["A"] * 10 + ["B"] * 21}
+    m = P.Leida.from_arrays(ts, classes).fit_predict(TR=1.0, random_state=1, K_min=2, K_max=3, n_init=1)
+    ref = O.execute_all(ts, classes, TR=1.0, K_min=2, K_max=3, n_init=1, random_state=1)
+    assert eig_ok(m.eigenvectors.iloc[:, 2:].values, ref["eigenvectors"])
+    assert list(m.eigenvectors.condition) == list(ref["condition"])
+    for k in (2, 3):
+        assert np.array_equal(m.predictions[f"k_{k}"].values, ref["models"][k].labels_)
+        tab = m.occupancies(k)
+        assert list(zip(tab.subject_id, tab.condition)) == ref["metrics"][k]["rows"]
+        assert np.array_equal(tab.iloc[:, 2:].values, ref["metrics"][k]["occupancies"])
+        assert np.array_equal(m.transitions(k).iloc[:, 2:].values, ref["metrics"][k]["transitions"])
+        assert np.array_equal(m.dwell_times(k).iloc[:, 2:].values, ref["metrics"][k]["dwell_times"])
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
