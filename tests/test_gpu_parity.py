@@ -184,7 +184,7 @@ def test_kmeans_vs_oracle_config1(P, O, kind, N, S, T):
         for mode in ("exact", "reference"):
             km = P.clustering.KMeansLeida(k=k, n_init=2).fit(X, init_indices=inits[k], centroid_update=mode, engine=eng)
             assert np.array_equal(km.labels_, ref.labels_), (k, mode)
-            assert km.inertia_ == pytest.approx(ref.inertia_, rel=1e-9)
+            assert km.inertia_ == pytest.approx(ref.inertia_, rel=1e-6 if mode == "exact" else 1e-12)
             assert km.n_passes_ == ref.n_iter_runs_[km.best_init_] + 1
             if mode == "reference":
                 assert np.array_equal(km.cluster_centers_, ref.cluster_centers_)
@@ -199,7 +199,7 @@ def test_kmeans_large_k_and_wide_rows(P, O):
         ref = O.KMeansLeida(k=k, n_init=1, n_iter=6).fit(X, init_indices=idx)
         km = P.clustering.KMeansLeida(k=k, n_init=1, n_iter=6).fit(X, init_indices=idx, centroid_update="reference")
         assert np.array_equal(km.labels_, ref.labels_), k
-        assert km.inertia_ == pytest.approx(ref.inertia_, rel=1e-9)
+        assert km.inertia_ == pytest.approx(ref.inertia_, rel=1e-12)
 
 
 def test_kmeans_properties_large(P):
