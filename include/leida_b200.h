@@ -36,6 +36,8 @@ int         leida_version(void);
 const char* leida_last_error(void);
 /* number of SMs of the current device (grid sizing is derived from it) */
 int         leida_device_sm_count(void);
+/* kernels launched by this library in this process so far (monotonic counter, for bench.py) */
+int64_t     leida_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Stage 1 -- hilbert_phase          (signal_tools/_signal_tools.py:24-44)
@@ -145,13 +147,23 @@ int leida_kmeans_init(const float* X_init, int64_t xi_pitch, const int64_t* init
  * row whose top-2 margin is inside the fp32 error bound, so labels equal the fp64 argmin.  Rows
  * whose label changed move their fixed-point contribution between clusters in `acc`.
  * kmax (host value) = max K over the runs of this call; it selects the register tile, so callers
- * group runs of similar K.  worklist: device int32 (2*worklist_cap + 8) scratch for the fp64
- * re-check (rows that do not fit are resolved inline, slower but identical). */
+ * group runs of similar K.  worklist: device int32 (2*worklist_cap + 8), header zeroed once by the
+ * caller: rows the fp32 pass cannot decide are queued there (rows that do not fit are resolved
+ * inline, slower but identical) and MUST be resolved by leida_kmeans_recheck on the same stream
+ * before the next leida_kmeans_assign / leida_kmeans_update. */
 int leida_kmeans_assign(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                         int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
                         const float* cent, const double* cnorm, int64_t* acc,
                         int32_t* labels, int64_t* state,
                         int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
+
+/* fp64 re-evaluation of the queued rows with the reference's arithmetic order (scipy cdist
+ * 'cosine': sequential dot, dot/(|u||v|), clip, 1-cos; first minimum); empties the queue. */
+int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
+                         const int32_t* run_k, const int32_t* run_crow0,
+                         const float* cent, const double* cnorm, int64_t* acc,
+                         int32_t* labels, int64_t* state,
+                         int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
 
 /* Convergence bookkeeping + centroid update of every active run (clustering/_clustering.py:118-133):
  * a run stops when a pass at Lloyd iteration >= 1 changed no label, or after n_iter iterations;

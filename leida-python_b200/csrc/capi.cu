@@ -1,6 +1,7 @@
 // Library-level pieces of the C-ABI: version, error string, device queries.
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace leida {
 
@@ -12,6 +13,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 struct DevInfo {
     int sms = 0;
@@ -39,3 +43,4 @@ int max_smem_optin() { int s = dev_info().smem_optin; return s > 0 ? s : 227 * 1
 extern "C" int leida_version(void) { return 100; }
 extern "C" const char* leida_last_error(void) { return leida::g_err; }
 extern "C" int leida_device_sm_count(void) { return leida::sm_count(); }
+extern "C" int64_t leida_launch_count(void) { return leida::g_launches.load(); }

@@ -12,7 +12,10 @@ void set_error(const char* fmt, ...);
 int  sm_count();
 int  max_smem_optin();
 
-inline int check_launch(const char* what) {
+void count_launches(int n);
+
+inline int check_launch(const char* what, int n_launched = 1) {
+    count_launches(n_launched);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));

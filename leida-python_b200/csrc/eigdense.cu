@@ -262,5 +262,5 @@ extern "C" int leida_eigvec_dense_f64(const double* dfc, int N, int n_vol, doubl
         k_dense_roll_info<<<1, 1, 0, st>>>(info, it);
     }
     k_dense_finalize<<<(Tp + 31) / 32, 256, 0, st>>>(V, N, Tp, out, out_pitch);
-    return check_launch("leida_eigvec_dense_f64");
+    return check_launch("leida_eigvec_dense_f64", 3 + 4 * max_iter);
 }

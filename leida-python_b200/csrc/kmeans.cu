@@ -276,6 +276,16 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
         }
         if (lane == 0) atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
     }
+    // the last CTA to finish clears the list header for the next assign launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(&p.worklist[1], 1);
+        if (ticket == (int)gridDim.x - 1) {
+            p.worklist[0] = 0;
+            p.worklist[1] = 0;
+        }
+    }
 }
 
 __global__ void k_row_norms(const float* __restrict__ X, long long M, int N, long long XP, double* __restrict__ xnorm) {
@@ -621,7 +631,6 @@ extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t 
     // fp32 error bound of score = fl(dot)*fl(1/|c|): (n+2) roundings of relative size 2^-24 on
     // sum |x_j c_j| <= |x||c|, doubled for the difference of two scores, 10% slack.
     p.tau0 = 2.2f * (float)(x_pitch + 8) * 5.9604645e-8f;
-    LEIDA_CUDA_TRY(cudaMemsetAsync(worklist, 0, 8 * sizeof(int32_t), st));
     if (kmax <= 4) rc = launch_assign<4, 2>(p, n_runs, st);
     else if (kmax <= 8) rc = launch_assign<8, 2>(p, n_runs, st);
     else if (kmax <= 12) rc = launch_assign<12, 2>(p, n_runs, st);
@@ -632,8 +641,21 @@ extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t 
     else if (kmax <= 40) rc = launch_assign<40, 2>(p, n_runs, st);
     else if (kmax <= 48) rc = launch_assign<48, 1>(p, n_runs, st);
     else rc = launch_assign<64, 1>(p, n_runs, st);
-    if (rc) return rc;
-    k_recheck<<<sm_count() * 4, 128, 0, st>>>(p);
+    return rc;
+}
+
+extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
+                                    const int32_t* run_k, const int32_t* run_crow0, const float* cent,
+                                    const double* cnorm, int64_t* acc, int32_t* labels, int64_t* state,
+                                    int32_t* worklist, int64_t worklist_cap, leida_stream_t stream) {
+    LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && acc && labels && state && worklist, "null pointer");
+    LEIDA_REQUIRE(N >= 1 && x_pitch >= N && x_pitch % 32 == 0, "x_pitch multiple of 32 and >= N");
+    AssignParams p;
+    p.X = X; p.xnorm = xnorm; p.M = M; p.N = N; p.XP = (int)x_pitch;
+    p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
+    p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
+    p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f;
+    k_recheck<<<sm_count() * 4, 128, 0, (cudaStream_t)stream>>>(p);
     return check_launch("k_recheck");
 }
 
@@ -665,7 +687,7 @@ extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int6
         k_distortion<<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, run_k, run_crow0, cent, cnorm, labels,
                                            (long long*)state);
     }
-    return check_launch("k_distortion");
+    return check_launch("k_distortion", M > 0 ? 2 : 1);
 }
 
 extern "C" int leida_kmeans_means_f32_sequential(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs,

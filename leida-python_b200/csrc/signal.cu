@@ -454,7 +454,7 @@ extern "C" int leida_hilbert_phase_f64(const double* x, int64_t n_series, int T,
         plan = planL;
         threads = 256;
     }
-    int rc = check_launch("hilbert setup");
+    int rc = check_launch("hilbert setup", direct ? 1 : 3);
     if (rc) return rc;
     int per_sm = (int)((size_t)smem_max / (smem + 1024));
     if (per_sm < 1) per_sm = 1;

@@ -12,10 +12,9 @@ import warnings
 import numpy as np
 
 from . import _native as nv
-from .clustering.kmeans import KMeansEngine, identify_states
-from .dynamics_metrics.metrics import Segments, compute_dynamics_metrics
-from .parallel import Comm, row_offsets
-from .signal_tools.phase import leading_eigenvectors, padded_pitch
+from .dynamics_metrics.metrics import Segments
+from .parallel import Comm
+from .pipeline import run_device
 
 
 class Bunch(dict):
@@ -92,7 +91,7 @@ class Leida:
     # ------------------------------------------------------------------------------------------
     def fit_predict(self, TR=None, paired_tests=False, n_perm=5_000, save_results=False, random_state=None,
                     K_min=2, K_max=20, n_init=15, init_indices=None, centroid_update="exact",
-                    keep_eigenvectors=True):
+                    keep_eigenvectors=True, _profile=None):
         """_leida.py:111-192.  K range and n_init are arguments here (the reference hard-codes
         2..20 and 15, :156-157 / _clustering.py:250); paired_tests / n_perm are validated like the
         reference but the statistics stage is not run; save_results=True is not supported."""
@@ -109,11 +108,12 @@ class Leida:
         if save_results:
             warnings.warn("save_results=True: the results folder (SURVEY 8f-3) is not written by the GPU path")
         self._K_min_, self._K_max_ = int(K_min), int(K_max)
-        self._execute_all(TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors)
+        self._execute_all(TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, _profile)
         self._is_fitted = True
         return self
 
-    def _execute_all(self, TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors):
+    def _execute_all(self, TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, profile=None):
+        import pandas as pd
         torch = nv.require_cuda()
         dev = torch.device("cuda", torch.cuda.current_device())
         comm = self._comm if self._comm is not None else Comm()
@@ -122,13 +122,9 @@ class Leida:
         n_vols = [int(np.asarray(self.time_series[s]).shape[1]) - 2 for s in ids]
         if min(n_vols) < 1:
             raise Exception("every subject needs at least 3 volumes")
-        M = int(sum(n_vols))
-        xp = padded_pitch(N)
-        X32 = torch.empty((M, xp), dtype=torch.float32, device=dev)
-        lei64 = torch.empty((M, N), dtype=torch.float64, device=dev) if keep_eigenvectors else None
-        self.h2d_bytes = 0
-        # stage 1+2: consecutive subjects with the same T go through one fused call (_leida.py:279-289)
-        i, row = 0, 0
+        self.h2d_bytes = self.d2h_bytes = 0
+        # host -> device: consecutive subjects with the same T are staged as one pinned block
+        blocks, i = [], 0
         while i < len(ids):
             T = n_vols[i] + 2
             j = i
@@ -138,47 +134,55 @@ class Leida:
             hv = host.numpy()
             for b, s in enumerate(ids[i:j]):
                 hv[b] = self.time_series[s]
-            x = host.to(dev, non_blocking=True)
+            blocks.append(host.to(dev, non_blocking=True))
             self.h2d_bytes += host.numel() * 8
-            rows = (j - i) * (T - 2)
-            leading_eigenvectors(x, out_f64=None if lei64 is None else lei64[row:row + rows],
-                                 out_f32=X32[row:row + rows], want_f64=lei64 is not None)
-            row += rows
             i = j
-        # per-volume metadata (_leida.py:290-297)
+        # per-volume metadata (_leida.py:290-297) and the metric groups
         sub_list = np.repeat(np.asarray(ids, dtype=object), n_vols)
-        per_volume = any(len(self.classes[s]) > 1 for s in ids)
-        if per_volume:
+        if any(len(self.classes[s]) > 1 for s in ids):
             cond_list = np.concatenate([
                 np.asarray(self.classes[s], dtype=object)[1:nv_ + 1] if len(self.classes[s]) > 1
                 else np.repeat(np.asarray(self.classes[s][:1], dtype=object), nv_)
                 for s, nv_ in zip(ids, n_vols)])
             segments = Segments.from_arrays(sub_list.astype(str), cond_list.astype(str))
-            segments.subjects = list(segments.subjects)
         else:
             conds = [self.classes[s][0] for s in ids]
             cond_list = np.repeat(np.asarray(conds, dtype=object), n_vols)
             segments = Segments.contiguous(np.asarray(ids), np.asarray(conds), n_vols)
         self._meta = (sub_list, cond_list)
-        # stage 3 (_leida.py:314-321)
-        m_all = comm.all_gather_int(M)
-        off = row_offsets(m_all)
-        engine = KMeansEngine(X32, n_features=N, comm=comm, row_lo=int(off[comm.rank]), m_global=int(off[-1]))
-        import pandas as pd
-        meta = pd.DataFrame({"subject_id": sub_list, "condition": cond_list})
-        predictions, performance, models = identify_states(
-            meta, K_min=self._K_min_, K_max=self._K_max_, n_init=n_init, random_state=random_state, plot=False,
-            init_indices=init_indices, centroid_update=centroid_update, engine=engine)
-        self.kmeans_batch_ = identify_states.last_batch
-        # stage 4 (_leida.py:326-331)
-        Ks = [f"k_{k}" for k in range(self._K_min_, self._K_max_ + 1)]
-        dev_labels = torch.stack([models[k].labels_device_ for k in Ks])
-        dynamics = compute_dynamics_metrics(predictions, TR=TR, _segments=segments, _device_labels=dev_labels)
+        seg_off = torch.from_numpy(segments.off).to(dev)
+        seg_rows = torch.from_numpy(segments.rows).to(dev)
+        self.h2d_bytes += segments.off.nbytes + segments.rows.nbytes
+        res = run_device(blocks, N, seg_off, seg_rows, K_min=self._K_min_, K_max=self._K_max_, n_init=n_init,
+                         random_state=random_state, init_indices=init_indices, centroid_update=centroid_update,
+                         keep_f64=keep_eigenvectors, comm=comm, profile=profile)
+        self.device_result_ = res
+        self.kmeans_batch_ = res.batch
+        # device -> host: labels, centroids, integer metric tables, eigenvectors
+        ks = list(range(self._K_min_, self._K_max_ + 1))
+        labels = res.labels.cpu().numpy()
+        occ, runs, trans = res.occ.cpu().numpy(), res.runs.cpu().numpy(), res.trans.cpu().numpy()
+        self.d2h_bytes += labels.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
+        predictions = pd.DataFrame({"subject_id": sub_list, "condition": cond_list})
+        models, perf = {}, []
+        for c, k in enumerate(ks):
+            km = res.models[k]
+            km.labels_ = labels[c].astype(np.int64)
+            km.cluster_centers_ = km.centers_device_.cpu().numpy()
+            self.d2h_bytes += km.cluster_centers_.nbytes
+            models[f"k_{k}"] = km
+            predictions[f"k_{k}"] = km.labels_
+            perf.append({"k": k, "Dunn_score": np.nan, "distortion": km.inertia_, "silhouette_score": np.nan,
+                         "Davies-Bouldin_score": np.nan})
+        self._lei_host = None
+        if keep_eigenvectors:
+            self._lei_host = res.lei64.cpu().numpy()
+            self.d2h_bytes += self._lei_host.nbytes
+        from .dynamics_metrics.metrics import tables_from_counts
+        dynamics = tables_from_counts([f"k_{k}" for k in ks], res.col_k, segments, occ, runs, trans, TR)
         self.predictions = predictions
-        self._lei64 = lei64
         self._eigenvectors_df = None
-        self._engine = engine
-        self._clustering_ = Bunch(predictions=predictions, performance=performance, models=models)
+        self._clustering_ = Bunch(predictions=predictions, performance=pd.DataFrame(perf), models=models)
         self._dynamics_ = Bunch(dwell_times=dynamics["dwell_times"], occupancies=dynamics["occupancies"],
                                 transitions=dynamics["transitions"], stats=None)
         self._classes_lst_ = np.unique(cond_list.astype(str)).tolist()
@@ -191,9 +195,9 @@ class Leida:
         first access from the device copy."""
         import pandas as pd
         if getattr(self, "_eigenvectors_df", None) is None:
-            if getattr(self, "_lei64", None) is None:
+            if getattr(self, "_lei_host", None) is None:
                 raise Exception("eigenvectors were not kept (keep_eigenvectors=False) or the model is not fitted")
-            df = pd.DataFrame(self._lei64.cpu().numpy(), columns=self.rois_labels)
+            df = pd.DataFrame(self._lei_host, columns=self.rois_labels)
             df.insert(0, "subject_id", self._meta[0])
             df.insert(1, "condition", self._meta[1])
             self._eigenvectors_df = df

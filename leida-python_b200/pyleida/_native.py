@@ -29,6 +29,7 @@ SIGNATURES = {
     "leida_version": (c_int, []),
     "leida_last_error": (c_char_p, []),
     "leida_device_sm_count": (c_int, []),
+    "leida_launch_count": (c_int64, []),
     "leida_hilbert_workspace_bytes": (c_size_t, [c_int]),
     "leida_hilbert_phase_f64": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, c_int, c_int, _P, c_size_t, _P]),
     "leida_phase_coherence_f64": (c_int, [_P, c_int, c_int, c_int64, _P, _P]),
@@ -42,6 +43,7 @@ SIGNATURES = {
     "leida_kmeans_init": (c_int, [_P, c_int64, _P, c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P, c_int64, _P, _P]),
     "leida_kmeans_assign": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                     c_int64, _P]),
+    "leida_kmeans_recheck": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "leida_kmeans_update": (c_int, [c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, c_int, _P, _P]),
     "leida_kmeans_distortion": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_means_f32_sequential": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P]),
@@ -93,3 +95,7 @@ def stream():
 
 def call(name, *args):
     check(getattr(lib, name)(*args), name)
+
+
+def launch_count():
+    return int(lib.leida_launch_count())

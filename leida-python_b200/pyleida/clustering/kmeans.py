@@ -56,8 +56,10 @@ class KMeansEngine:
         nv.call("leida_kmeans_row_norms", nv.ptr(X), self.M, N, xp, nv.ptr(self.xnorm), nv.stream())
 
     # ------------------------------------------------------------------------------------------
-    def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1):
-        """runs: list of (k, init_rows) with init_rows = k global row indices.  Returns BatchResult."""
+    def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1, profile=None):
+        """runs: list of (k, init_rows) with init_rows = k global row indices.  Returns BatchResult.
+        profile: optional list; (start, stop) CUDA event pairs bracketing every assign-kernel launch
+        are appended to it (bench.py's live roofline measurement)."""
         torch = self.torch
         if centroid_update not in ("exact", "reference"):
             raise ValueError("centroid_update must be 'exact' or 'reference'")
@@ -90,6 +92,7 @@ class KMeansEngine:
         state = torch.empty((R, nv.STATE_WORDS), dtype=torch.int64, device=dev)
         cap = int(min(max(self.M // 4, 1 << 16), 1 << 24))
         worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
+        worklist[:8].zero_()
         n_active = torch.zeros(1, dtype=torch.int32, device=dev)
         st = nv.stream()
 
@@ -116,7 +119,17 @@ class KMeansEngine:
         launches = 0
         while True:
             for (a, b, kmax) in groups:
+                if profile is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 nv.call("leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
+                        run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
+                        labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
+                        nv.ptr(worklist), cap, st)
+                if profile is not None:
+                    e1.record()
+                    profile.append((e0, e1))
+                nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
                         nv.ptr(worklist), cap, st)
@@ -300,7 +313,7 @@ class KMeansLeida:
         self._finish(eng, res, [uniq.index(f) for f in first])
         return self
 
-    def _finish(self, eng, res, run_of_init):
+    def _finish(self, eng, res, run_of_init, to_host=True):
         inertias = [res.inertia(r) for r in run_of_init]
         best_init = _select_best(inertias)
         r = run_of_init[best_init]
@@ -310,8 +323,10 @@ class KMeansLeida:
         lut_d = torch.from_numpy(lut).to(lab.device)
         nv.call("leida_remap_labels_i32", nv.ptr(lab), lab.numel(), nv.ptr(lut_d), len(lut), nv.stream())
         self.labels_device_ = lab
-        self.labels_ = lab.cpu().numpy().astype(np.int64)
-        self.cluster_centers_ = res.centers_device(r).cpu().numpy()[order, :]
+        self.centers_device_ = res.centers_device(r)[torch.from_numpy(np.ascontiguousarray(order)).to(lab.device)]
+        if to_host:
+            self.labels_ = lab.cpu().numpy().astype(np.int64)
+            self.cluster_centers_ = self.centers_device_.cpu().numpy()
         self.inertia_ = np.float64(inertias[best_init])
         self.n_passes_ = res.passes(r)
         self.inertia_runs_ = inertias
@@ -341,6 +356,37 @@ class KMeansLeida:
         return eng.predict(self.cluster_centers_).cpu().numpy().astype(np.int64)
 
 
+def sweep_runs(M, K_min, K_max, n_init, random_state=None, init_indices=None):
+    """The (K, initial rows) runs of a K sweep in the reference's draw order (clustering/_clustering.py:
+    318-329), identical restarts removed.  Returns (runs, plan): plan[k][r] = index into runs of
+    restart r of K=k."""
+    if M > 30_000 and init_indices is None:
+        # :318-320 -- the reference draws its score sub-sample here; repeating the draw keeps the
+        # global RNG stream (and therefore every later initial centroid) aligned with it.
+        np.random.choice(np.arange(M), size=30_000, replace=False)
+    runs, plan = [], {}
+    for k in range(K_min, K_max + 1):                                          # :326
+        inits = list(init_indices[k]) if init_indices is not None else _draw_inits(M, k, n_init, random_state)
+        if len(inits) != n_init:
+            raise ValueError(f"init_indices[{k}] must hold n_init index arrays")
+        first = _dedupe(inits)
+        uniq = sorted(set(first))
+        base = len(runs)
+        runs.extend((k, inits[i]) for i in uniq)
+        plan[k] = [base + uniq.index(f) for f in first]
+    return runs, plan
+
+
+def select_models(engine, res, plan, n_init, to_host=True):
+    """Best restart per K (:139-146) + relabelling (:234-247) -> {k: fitted KMeansLeida}."""
+    models = {}
+    for k, run_of_init in plan.items():
+        km = KMeansLeida(k=k, n_init=n_init, n_iter=1_000)
+        km._finish(engine, res, run_of_init, to_host=to_host)
+        models[k] = km
+    return models
+
+
 def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=None, plot=True, save_results=False,
                     path=None, init_indices=None, centroid_update="exact", engine=None, scores=False):
     """K sweep of clustering/_clustering.py:250-374 with every (K, restart) run advanced in
@@ -359,24 +405,12 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
     if engine is None:
         X = np.array(eigens_dataset.iloc[:, 2:], dtype=np.float32)            # :316
         engine = KMeansEngine(X)
-    M = engine.m_global
-    if M > 30_000 and init_indices is None:
-        # :318-320 -- the reference draws its score sub-sample here; repeating the draw keeps the
-        # global RNG stream (and therefore every later initial centroid) aligned with it.
-        np.random.choice(np.arange(M), size=30_000, replace=False)
-    runs, plan = [], {}
-    for k in range(K_min, K_max + 1):                                          # :326
-        inits = list(init_indices[k]) if init_indices is not None else _draw_inits(M, k, n_init, random_state)
-        first = _dedupe(inits)
-        uniq = sorted(set(first))
-        base = len(runs)
-        runs.extend((k, inits[i]) for i in uniq)
-        plan[k] = [base + uniq.index(f) for f in first]
+    runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices)
     res = engine.run(runs, n_iter=1_000, centroid_update=centroid_update)
+    by_k = select_models(engine, res, plan, n_init)
     models, perf = {}, []
     for k in range(K_min, K_max + 1):
-        km = KMeansLeida(k=k, n_init=n_init, n_iter=1_000)
-        km._finish(engine, res, plan[k])
+        km = by_k[k]
         models[f"k_{k}"] = km
         perf.append({"k": k, "Dunn_score": np.nan, "distortion": km.inertia_, "silhouette_score": np.nan,
                      "Davies-Bouldin_score": np.nan})

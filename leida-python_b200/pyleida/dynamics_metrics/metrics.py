@@ -229,10 +229,15 @@ def compute_dynamics_metrics(clusters_labels, TR=None, save_results=False, path=
         col_k.append(len(u))
     lab = _device_labels if _device_labels is not None else np.ascontiguousarray(ys.T, dtype=np.int32)
     occ, runs, trans = dynamics_counts(lab, col_k, seg)
+    return tables_from_counts(Ks, col_k, seg, occ, runs, trans, TR)
+
+
+def tables_from_counts(names, col_k, seg, occ, runs, trans, TR=None):
+    """The reference's three DataFrames per K column from the integer tables of dynamics_counts()."""
     lengths = np.diff(seg.off)
     out = {"dwell_times": {}, "occupancies": {}, "transitions": {}}
-    for i, name in enumerate(Ks):
-        k = col_k[i]
+    for i, name in enumerate(names):
+        k = int(col_k[i])
         out["occupancies"][name] = _state_frame(seg, _occupancy(occ[i][:, :k], lengths), k)
         out["dwell_times"][name] = _state_frame(seg, _dwell(occ[i][:, :k], runs[i][:, :k], TR), k)
         out["transitions"][name] = _transition_frame(seg, _transitions(trans[i][:, :k, :k]), k)
