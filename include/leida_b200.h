@@ -115,7 +115,7 @@ int    leida_eigvec_dense_f64(const double* dfc, int N, int n_vol, double* out, 
  * leida_kmeans_update.
  * ------------------------------------------------------------------------------------------ */
 #define LEIDA_KM_FRAC_BITS     40
-#define LEIDA_KM_STATE_WORDS   8
+#define LEIDA_KM_STATE_WORDS   16
 #define LEIDA_KM_ST_CHANGED    0   /* rows whose label changed in the last pass     (reducible) */
 #define LEIDA_KM_ST_DIST_HI    1   /* distortion, 2^-40 units                        (reducible) */
 #define LEIDA_KM_ST_DIST_LO    2   /* distortion remainder, 2^-80 units              (reducible) */
@@ -124,6 +124,8 @@ int    leida_eigvec_dense_f64(const double* dfc, int N, int n_vol, double* out, 
 #define LEIDA_KM_ST_PASSES     5   /* assignment passes done (initial pass included)              */
 #define LEIDA_KM_ST_EMPTY      6   /* 1 + index of the first empty cluster seen, 0 = none         */
 #define LEIDA_KM_ST_K          7   /* K of the run (set by leida_kmeans_init)                     */
+#define LEIDA_KM_ST_RECHECK_TOTAL 8  /* rows re-evaluated in fp64 over all passes (global count)    */
+#define LEIDA_KM_ST_CHANGED_TOTAL 9  /* label changes over all passes (global count)                */
 
 #define LEIDA_KM_MAX_K         64
 
@@ -163,7 +165,41 @@ int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, 
                          const int32_t* run_k, const int32_t* run_crow0,
                          const float* cent, const double* cnorm, int64_t* acc,
                          int32_t* labels, int64_t* state,
-                         int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
+                         int32_t* worklist, int64_t worklist_cap, int32_t* labels_out, leida_stream_t stream);
+/* labels_out == NULL: the exact label replaces labels[run][row] and the row's contribution is moved
+ * in acc (SIMT flow).  labels_out != NULL: the exact label is written to labels_out[run][row] only
+ * (tensor-core flow; leida_kmeans_tc_apply does the moves). */
+
+/* ---- tensor-core assignment flow (tcgen05 / TMEM / TMA) -------------------------------------
+ * Same semantics as leida_kmeans_assign for ALL active runs in one launch:
+ *   S = X * C'^T on the tensor cores with bf16 x 3 split operands (fp32-grade products), fused
+ *   top-2 epilogue, fp64 re-check of every row inside the error bound.  Per pass:
+ *     leida_kmeans_tc_assign  -> labels_new (label, or -2 = queued for the re-check)
+ *     leida_kmeans_recheck(labels_out = labels_new)
+ *     leida_kmeans_tc_apply   -> changed counts, fixed-point moves in acc, labels_cur := labels_new
+ *     [all-reduce acc/state]  leida_kmeans_update
+ *     leida_kmeans_tc_plan    -> packs the still-active runs' unit-normalised centroids for the next pass
+ * X1/X2: bf16 (M, tc_pitch) split of X (leida_kmeans_tc_split_rows, once per data set).
+ * C1/C2: bf16 (c_rows, tc_pitch) packed centroid operands; c_rows >= 128 * (number of tiles), a
+ *        bound is 2*sum(K) + 128.  plan (2), tile_first/tile_count (c_rows/128), prun/pcol/run_pcol
+ *        (n_runs): int32 device arrays owned by the caller, written by leida_kmeans_tc_plan. */
+int64_t leida_kmeans_tc_pitch(int N);
+int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch, void* X1, void* X2,
+                               leida_stream_t stream);
+int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int32_t* run_crow0, const int64_t* state,
+                         const float* cent, const double* cnorm, int N, int64_t x_pitch,
+                         int32_t* plan, int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol,
+                         int32_t* run_pcol, void* C1, void* C2, leida_stream_t stream);
+int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64_t x_pitch, const double* xnorm,
+                           int64_t M, int N, const void* C1, const void* C2, int64_t c_rows,
+                           const float* cent, const double* cnorm,
+                           const int32_t* plan, const int32_t* tile_first, const int32_t* tile_count,
+                           const int32_t* prun, const int32_t* pcol, const int32_t* run_k, const int32_t* run_crow0,
+                           int32_t* labels_new, int64_t* state, int32_t* worklist, int64_t worklist_cap,
+                           leida_stream_t stream);
+int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs, const int32_t* run_crow0,
+                          int32_t* labels_cur, const int32_t* labels_new, int64_t* acc, int64_t* state,
+                          leida_stream_t stream);
 
 /* Convergence bookkeeping + centroid update of every active run (clustering/_clustering.py:118-133):
  * a run stops when a pass at Lloyd iteration >= 1 changed no label, or after n_iter iterations;

@@ -41,6 +41,19 @@ inline int check_launch(const char* what, int n_launched = 1) {
         }                                                                           \
     } while (0)
 
+// Sequential fp64 dot product in the reference's order (scipy cdist 'cosine'; no FMA contraction).
+__device__ __forceinline__ double dot_seq(const float* __restrict__ a, const float* __restrict__ b, int n) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s = __dadd_rn(s, __dmul_rn((double)a[j], (double)b[j]));
+    return s;
+}
+
+__device__ __forceinline__ double cosine_distance(double dot, double na, double nb) {
+    double c = dot / (na * nb);
+    if (fabs(c) > 1.0) c = copysign(1.0, c);
+    return 1.0 - c;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -33,19 +33,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Sequential fp64 dot product in the reference's order (no FMA contraction).
-__device__ __forceinline__ double dot_seq(const float* __restrict__ a, const float* __restrict__ b, int n) {
-    double s = 0.0;
-    for (int j = 0; j < n; ++j) s = __dadd_rn(s, __dmul_rn((double)a[j], (double)b[j]));
-    return s;
-}
-
-__device__ __forceinline__ double cosine_distance(double dot, double na, double nb) {
-    double c = dot / (na * nb);
-    if (fabs(c) > 1.0) c = copysign(1.0, c);
-    return 1.0 - c;
-}
-
 struct AssignParams {
     const float* X;
     const double* xnorm;
@@ -62,6 +49,7 @@ struct AssignParams {
     int32_t* worklist;  // [0] = count, entries (run,row) from worklist+8
     long long worklist_cap;
     float tau0;
+    int32_t* labels_out;  // recheck only: when set, write the exact label here and leave the move to the caller
 };
 
 // Move one row's fixed-point contribution between clusters.  Called by `nthreads` cooperating
@@ -264,6 +252,13 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
             if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
         }
         if (bk == 0x7fffffff) bk = 0;   // every distance NaN: numpy's argmin returns the first index
+        if (p.labels_out) {
+            if (lane == 0) {
+                p.labels_out[(long long)run * p.M + row] = bk;
+                atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
+            }
+            continue;
+        }
         int32_t* lab = p.labels + (long long)run * p.M;
         const int old_l = lab[row];
         __syncwarp();
@@ -369,6 +364,8 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             const long long p = st[LEIDA_KM_ST_PASSES];  // index of the pass that just finished
             st[LEIDA_KM_ST_PASSES] = p + 1;
             const long long changed = state_red[(long long)run * kStateWords + LEIDA_KM_ST_CHANGED];
+            st[LEIDA_KM_ST_CHANGED_TOTAL] += changed;
+            st[LEIDA_KM_ST_RECHECK_TOTAL] += state_red[(long long)run * kStateWords + LEIDA_KM_ST_RECHECKED];
             // pass p >= 1 is Lloyd iteration p-1; the reference tests convergence from iteration 1 on
             // (clustering/_clustering.py:129-132) and runs at most n_iter iterations (:118).
             if ((p >= 2 && changed == 0) || p >= n_iter) st[LEIDA_KM_ST_ACTIVE] = 0;
@@ -627,7 +624,7 @@ extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t 
     p.X = X; p.xnorm = xnorm; p.M = M; p.N = N; p.XP = (int)x_pitch;
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
-    p.worklist = worklist; p.worklist_cap = worklist_cap;
+    p.worklist = worklist; p.worklist_cap = worklist_cap; p.labels_out = nullptr;
     // fp32 error bound of score = fl(dot)*fl(1/|c|): (n+2) roundings of relative size 2^-24 on
     // sum |x_j c_j| <= |x||c|, doubled for the difference of two scores, 10% slack.
     p.tau0 = 2.2f * (float)(x_pitch + 8) * 5.9604645e-8f;
@@ -647,14 +644,15 @@ extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t 
 extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                                     const int32_t* run_k, const int32_t* run_crow0, const float* cent,
                                     const double* cnorm, int64_t* acc, int32_t* labels, int64_t* state,
-                                    int32_t* worklist, int64_t worklist_cap, leida_stream_t stream) {
+                                    int32_t* worklist, int64_t worklist_cap, int32_t* labels_out,
+                                    leida_stream_t stream) {
     LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && acc && labels && state && worklist, "null pointer");
     LEIDA_REQUIRE(N >= 1 && x_pitch >= N && x_pitch % 32 == 0, "x_pitch multiple of 32 and >= N");
     AssignParams p;
     p.X = X; p.xnorm = xnorm; p.M = M; p.N = N; p.XP = (int)x_pitch;
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
-    p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f;
+    p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out;
     k_recheck<<<sm_count() * 4, 128, 0, (cudaStream_t)stream>>>(p);
     return check_launch("k_recheck");
 }

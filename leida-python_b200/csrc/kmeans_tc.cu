@@ -1,0 +1,492 @@
+// Tensor-core assignment pass of the lock-step k-means (sm_100a: TMA + tcgen05.mma + TMEM).
+//
+// The distance step of every active run is one contraction  S = X (M x N) * C'^T (N x sum K),
+// C' = unit-normalised centroids of all active runs packed side by side (clustering/_clustering.py:127
+// evaluated for every run at once).  fp32 operands are split into bf16 pairs (v = v1 + v2 + r,
+// |r| <= 2^-18 |v|) and the product is accumulated as X1*C1 + X1*C2 + X2*C1 in fp32 in TMEM, which
+// reproduces the fp32 product to ~2^-16 relative; the epilogue takes the top-2 scores per (row, run),
+// trusts the argmax only when the margin exceeds a rigorous error bound and queues the other rows for
+// the fp64 re-check (leida_kmeans_recheck), so labels are still the fp64 argmin of the reference.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..5 epilogue
+// (one TMEM lane quarter each).  Persistent over row tiles of 128 rows; for every row tile all column
+// tiles (128 packed centroid columns) are visited, K streamed in 64-element (128-byte, swizzled) blocks.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace leida {
+
+constexpr int kStateWordsTc = LEIDA_KM_STATE_WORDS;
+constexpr int BM = 128;          // rows per tile  (UMMA M)
+constexpr int BN = 128;          // packed centroid columns per tile (UMMA N)
+constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int ST = 2;            // smem pipeline stages
+constexpr int STAGE_BYTES = 4 * BM * BK * 2;          // X1, X2, C1, C2 blocks: 64 KB
+constexpr int SCORE_PITCH = BN + 1;                   // floats; odd pitch: row-per-thread access is conflict free
+constexpr int TMEM_COLS = 256;                        // two fp32 accumulators of BN columns
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n.reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.b32 %0, 1, 0, P1;\n}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && spin > (1u << 26)) __trap();   // a lost arrival must fail loudly, not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle, dense 8-row groups (1024 B): see cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t umma_desc(const void* tile) {
+    const uint64_t addr = (uint64_t)(smem_u32(tile) & 0x3FFFF) >> 4;
+    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Packing plan written by k_plan (device), read by the assign kernel.
+//   plan[0] = number of column tiles, plan[1] = number of packed (active) runs
+//   tile_first[t], tile_count[t] : slice of the packed run list that lives in tile t
+//   prun[i] = run id, pcol[i] = first column of the run inside its tile
+struct TcParams {
+    long long M;
+    int nkb;   // k-blocks = NPK / 64
+    const int32_t* plan;
+    const int32_t* tile_first;
+    const int32_t* tile_count;
+    const int32_t* prun;
+    const int32_t* pcol;
+    const int32_t* run_k;
+    const double* xnorm;
+    float tau;
+    int32_t* labels_new;
+    int32_t* worklist;
+    long long worklist_cap;
+    // for the (slow, exact) inline resolution when the work list is full
+    const float* X;
+    int XP;
+    int N;
+    const float* cent;
+    const double* cnorm;
+    const int32_t* run_crow0;
+    long long* state;
+};
+
+__global__ void __launch_bounds__(192, 1)
+k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+            const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* stages = base;                                         // ST * 64 KB
+    float* scores = reinterpret_cast<float*>(base + ST * STAGE_BYTES);    // BM * SCORE_PITCH floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scores + BM * SCORE_PITCH + 4);
+    uint64_t* full = bars;            // [ST]
+    uint64_t* empty = bars + ST;      // [ST]
+    uint64_t* tfull = bars + 2 * ST;  // [2]
+    uint64_t* tempty = tfull + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_ct = p.plan[0];
+    const int n_rt = (int)((p.M + BM - 1) / BM);
+
+    if (warp == 0) {
+        if (lane == 0 && n_ct > 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x)
+                for (int ct = 0; ct < n_ct; ++ct)
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        unsigned char* s = stages + stage * STAGE_BYTES;
+                        mbar_expect_tx(&full[stage], STAGE_BYTES);
+                        tma_load_2d(s, &tmX1, &full[stage], kb * BK, rt * BM);
+                        tma_load_2d(s + 16384, &tmX2, &full[stage], kb * BK, rt * BM);
+                        tma_load_2d(s + 32768, &tmC1, &full[stage], kb * BK, ct * BN);
+                        tma_load_2d(s + 49152, &tmC2, &full[stage], kb * BK, ct * BN);
+                        if (++stage == ST) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && n_ct > 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x)
+                for (int ct = 0; ct < n_ct; ++ct) {
+                    mbar_wait(&tempty[acc], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + acc * BN;
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        unsigned char* s = stages + stage * STAGE_BYTES;
+                        const uint64_t a1 = umma_desc(s), a2 = umma_desc(s + 16384);
+                        const uint64_t b1 = umma_desc(s + 32768), b2 = umma_desc(s + 49152);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            tc_mma_bf16(d, a1 + 2 * k, b1 + 2 * k, (kb | k) ? 1u : 0u);
+                            tc_mma_bf16(d, a1 + 2 * k, b2 + 2 * k, 1u);
+                            tc_mma_bf16(d, a2 + 2 * k, b1 + 2 * k, 1u);
+                        }
+                        tc_commit(&empty[stage]);
+                        if (++stage == ST) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&tfull[acc]);
+                    acc ^= 1;
+                    if (acc == 0) aphase ^= 1;
+                }
+        }
+    } else if (n_ct > 0) {
+        const int q = warp & 3;                       // TMEM lane quarter this warp may touch
+        const int r_in_tile = q * 32 + lane;
+        float* my = scores + r_in_tile * SCORE_PITCH;
+        int acc = 0;
+        uint32_t aphase = 0;
+        for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
+            const long long row = (long long)rt * BM + r_in_tile;
+            const bool valid = row < p.M;
+            const float thr = valid ? p.tau * (float)p.xnorm[row] : 0.f;
+            for (int ct = 0; ct < n_ct; ++ct) {
+                mbar_wait(&tfull[acc], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) my[c * 32 + j] = v[j];
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty[acc]);            // accumulator may be overwritten by the next tile
+                acc ^= 1;
+                if (acc == 0) aphase ^= 1;
+                const int first = p.tile_first[ct], cnt = p.tile_count[ct];
+                for (int i = first; i < first + cnt; ++i) {
+                    const int run = p.prun[i], c0 = p.pcol[i], K = p.run_k[run];
+                    float best = -INFINITY, second = -INFINITY;
+                    int bk = 0;
+                    for (int k = 0; k < K; ++k) {
+                        const float s = my[c0 + k];
+                        const bool gt = s > best;
+                        second = gt ? best : fmaxf(second, s);
+                        bk = gt ? k : bk;
+                        best = gt ? s : best;
+                    }
+                    if (valid) {
+                        int out = bk;
+                        if (!((best - second) > thr)) {
+                            out = -2;
+                            const int slot = atomicAdd(p.worklist, 1);
+                            if (slot < p.worklist_cap) {
+                                p.worklist[8 + 2 * (long long)slot] = run;
+                                p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
+                            } else {
+                                const int crow0 = p.run_crow0[run];
+                                const float* xr = p.X + row * p.XP;
+                                const double xnd = p.xnorm[row];
+                                double bd = INFINITY;
+                                out = 0;
+                                for (int k = 0; k < K; ++k) {
+                                    const double d = cosine_distance(
+                                        dot_seq(xr, p.cent + (long long)(crow0 + k) * p.XP, p.N), xnd, p.cnorm[crow0 + k]);
+                                    if (d < bd) { bd = d; out = k; }
+                                }
+                                atomicAdd(reinterpret_cast<unsigned long long*>(
+                                              p.state + (long long)run * kStateWordsTc + LEIDA_KM_ST_RECHECKED), 1ull);
+                            }
+                        }
+                        p.labels_new[(long long)run * p.M + row] = out;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ---- operand preparation ----------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// X fp32 (M, XP) -> X1, X2 bf16 (M, NPK); columns >= N are zero.
+__global__ void k_split_rows(const float* __restrict__ X, long long M, int N, long long XP, __nv_bfloat16* __restrict__ X1,
+                             __nv_bfloat16* __restrict__ X2, int NPK) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * NPK) return;
+    const long long r = i / NPK;
+    const int j = (int)(i - r * NPK);
+    const float v = j < N ? X[r * XP + j] : 0.f;
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    X1[i] = hi;
+    X2[i] = lo;
+}
+
+// Packing plan: active runs, in run order, placed side by side so that no run straddles a BN-column tile.
+__global__ void k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restrict__ state,
+                       int32_t* plan, int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol,
+                       int32_t* run_pcol) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int tile = 0, col = 0, np = 0, first = 0;
+    for (int r = 0; r < n_runs; ++r) {
+        run_pcol[r] = -1;
+        if (state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) continue;
+        const int K = run_k[r];
+        if (col + K > BN) {
+            tile_first[tile] = first;
+            tile_count[tile] = np - first;
+            ++tile;
+            col = 0;
+            first = np;
+        }
+        prun[np] = r;
+        pcol[np] = col;
+        run_pcol[r] = tile * BN + col;
+        col += K;
+        ++np;
+    }
+    if (np > first) {
+        tile_first[tile] = first;
+        tile_count[tile] = np - first;
+        ++tile;
+    }
+    plan[0] = tile;
+    plan[1] = np;
+}
+
+// Unit-normalised, bf16-split centroid rows of the active runs at their packed position.
+__global__ void k_pack_centroids(const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0,
+                                 const int32_t* __restrict__ run_pcol, const float* __restrict__ cent,
+                                 const double* __restrict__ cnorm, int N, int XP, __nv_bfloat16* __restrict__ C1,
+                                 __nv_bfloat16* __restrict__ C2, int NPK) {
+    const int run = blockIdx.x;
+    const int pc = run_pcol[run];
+    if (pc < 0) return;
+    const int K = run_k[run], crow0 = run_crow0[run];
+    for (int i = threadIdx.x; i < K * NPK; i += blockDim.x) {
+        const int k = i / NPK, j = i - k * NPK;
+        float v = 0.f;
+        if (j < N) {
+            const double cn = cnorm[crow0 + k];
+            const float inv = cn > 0.0 ? (float)(1.0 / cn) : 0.f;
+            v = cent[(long long)(crow0 + k) * XP + j] * inv;
+        }
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        C1[(long long)(pc + k) * NPK + j] = hi;
+        C2[(long long)(pc + k) * NPK + j] = lo;
+    }
+}
+
+// labels_cur vs labels_new of the active runs: count the changes, move the fixed-point row
+// contributions between clusters, and make the new labels current.
+__global__ void __launch_bounds__(256)
+k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ run_crow0,
+             int32_t* __restrict__ labels_cur, const int32_t* __restrict__ labels_new, long long* acc, long long* state) {
+    const int run = blockIdx.y;
+    if (state[(long long)run * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int crow0 = run_crow0[run];
+    const int AP = XP + 8;
+    int32_t* cur = labels_cur + (long long)run * M;
+    const int32_t* nw = labels_new + (long long)run * M;
+    const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x - lane);   // first row of this warp
+    const long long row = row0 + lane;
+    int o = 0, n = 0;
+    if (row < M) { o = cur[row]; n = nw[row]; }
+    const bool changed = (row < M) && (o != n);
+    unsigned mask = __ballot_sync(0xffffffffu, changed);
+    if (mask == 0) return;
+    if (changed) cur[row] = n;
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(state + (long long)run * kStateWordsTc + LEIDA_KM_ST_CHANGED),
+                             (unsigned long long)__popc(mask));
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int ob = __shfl_sync(0xffffffffu, o, b), nb = __shfl_sync(0xffffffffu, n, b);
+        const float* xr = X + (row0 + b) * XP;
+        long long* an = acc + (long long)(crow0 + nb) * AP;
+        long long* ao = acc + (long long)(crow0 + (ob < 0 ? 0 : ob)) * AP;
+        for (int j = lane; j < N; j += 32) {
+            const long long qv = __double2ll_rn((double)xr[j] * 1099511627776.0);
+            atomicAdd(reinterpret_cast<unsigned long long*>(an + j), (unsigned long long)qv);
+            if (ob >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(ao + j), (unsigned long long)(-qv));
+        }
+        if (lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(an + XP), 1ull);
+            if (ob >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(ao + XP), (unsigned long long)(-1ll));
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2D bf16 tensor (rows, NPK) row-major; box = 64 columns (128 B) x 128 rows, 128-byte swizzle.
+static int make_map(CUtensorMap* map, const void* ptr, long long rows, int NPK) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return LEIDA_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)NPK, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)NPK * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return LEIDA_ERR_CUDA; }
+    return LEIDA_OK;
+}
+
+}  // namespace leida
+
+using namespace leida;
+
+extern "C" int64_t leida_kmeans_tc_pitch(int N) { return ((int64_t)N + BK - 1) / BK * BK; }
+
+extern "C" int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch, void* X1, void* X2,
+                                          leida_stream_t stream) {
+    LEIDA_REQUIRE(X && X1 && X2, "null pointer");
+    LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N, "sizes");
+    const int NPK = (int)leida_kmeans_tc_pitch(N);
+    const long long n = M * NPK;
+    k_split_rows<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, M, N, x_pitch, (__nv_bfloat16*)X1,
+                                                                                 (__nv_bfloat16*)X2, NPK);
+    return check_launch("k_split_rows");
+}
+
+extern "C" int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int32_t* run_crow0, const int64_t* state,
+                                    const float* cent, const double* cnorm, int N, int64_t x_pitch, int32_t* plan,
+                                    int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol,
+                                    int32_t* run_pcol, void* C1, void* C2, leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(run_k && run_crow0 && state && cent && cnorm && plan && tile_first && tile_count && prun && pcol &&
+                      run_pcol && C1 && C2, "null pointer");
+    LEIDA_REQUIRE(n_runs >= 1 && N >= 1 && x_pitch >= N, "sizes");
+    const int NPK = (int)leida_kmeans_tc_pitch(N);
+    k_plan<<<1, 32, 0, st>>>(n_runs, run_k, (const long long*)state, plan, tile_first, tile_count, prun, pcol, run_pcol);
+    k_pack_centroids<<<n_runs, 256, 0, st>>>(run_k, run_crow0, run_pcol, cent, cnorm, N, (int)x_pitch, (__nv_bfloat16*)C1,
+                                             (__nv_bfloat16*)C2, NPK);
+    return check_launch("leida_kmeans_tc_plan", 2);
+}
+
+extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64_t x_pitch,
+                                      const double* xnorm, int64_t M, int N, const void* C1, const void* C2,
+                                      int64_t c_rows, const float* cent, const double* cnorm, const int32_t* plan,
+                                      const int32_t* tile_first, const int32_t* tile_count, const int32_t* prun,
+                                      const int32_t* pcol, const int32_t* run_k, const int32_t* run_crow0,
+                                      int32_t* labels_new, int64_t* state, int32_t* worklist, int64_t worklist_cap,
+                                      leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(X1 && X2 && X && xnorm && C1 && C2 && cent && cnorm && plan && tile_first && tile_count && prun && pcol &&
+                      run_k && run_crow0 && labels_new && state && worklist, "null pointer");
+    LEIDA_REQUIRE(M >= 1 && M < (1LL << 31) && N >= 1 && c_rows >= BN, "sizes");
+    const int NPK = (int)leida_kmeans_tc_pitch(N);
+    CUtensorMap mx1, mx2, mc1, mc2;
+    int rc;
+    if ((rc = make_map(&mx1, X1, M, NPK)) || (rc = make_map(&mx2, X2, M, NPK)) || (rc = make_map(&mc1, C1, c_rows, NPK)) ||
+        (rc = make_map(&mc2, C2, c_rows, NPK)))
+        return rc;
+    TcParams p;
+    p.M = M; p.nkb = NPK / BK; p.plan = plan; p.tile_first = tile_first; p.tile_count = tile_count;
+    p.prun = prun; p.pcol = pcol; p.run_k = run_k; p.xnorm = xnorm;
+    // Error bound of a score (|x| units): dropped split terms 3*2^-18, normalisation of c 2^-22, fp32
+    // accumulation of 3*NPK products in the tensor core (<= 2^-22 each, not assumed round-to-nearest);
+    // doubled for the difference of two scores, 25% slack.
+    p.tau = 2.5f * (3.0f * 3.8147e-6f + 2.4e-7f + 3.0f * (float)NPK * 2.3842e-7f);
+    p.labels_new = labels_new; p.worklist = worklist; p.worklist_cap = worklist_cap;
+    p.X = X; p.XP = (int)x_pitch; p.N = N; p.cent = cent; p.cnorm = cnorm; p.run_crow0 = run_crow0;
+    p.state = (long long*)state;
+    const size_t smem = 1024 + (size_t)ST * STAGE_BYTES + (size_t)(BM * SCORE_PITCH + 4) * sizeof(float) + 16 * sizeof(uint64_t);
+    LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_tc_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_rt = (int)((M + BM - 1) / BM);
+    const int grid = n_rt < sm_count() ? n_rt : sm_count();
+    k_tc_assign<<<grid, 192, smem, st>>>(mx1, mx2, mc1, mc2, p);
+    return check_launch("k_tc_assign");
+}
+
+extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs,
+                                     const int32_t* run_crow0, int32_t* labels_cur, const int32_t* labels_new,
+                                     int64_t* acc, int64_t* state, leida_stream_t stream) {
+    LEIDA_REQUIRE(X && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
+    LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && n_runs >= 1 && n_runs <= 65535, "sizes");
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)n_runs);
+    k_diff_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, run_crow0, labels_cur, labels_new,
+                                                          (long long*)acc, (long long*)state);
+    return check_launch("k_diff_apply");
+}

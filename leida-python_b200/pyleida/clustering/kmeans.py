@@ -5,6 +5,7 @@ reference does with numpy's *global legacy RNG* and tiny arrays: drawing the ini
 (:103-105), choosing the best restart (:139-146) and the relabelling permutation (:234-247).
 Everything that touches the (M, N) data runs in libleida_b200.so.
 """
+import os
 import warnings
 
 import numpy as np
@@ -14,6 +15,9 @@ from ..parallel import Comm, gather_seed_rows
 from ..signal_tools.phase import padded_pitch
 
 _KP_BUCKETS = (4, 8, 12, 16, 20, 24, 32, 40, 48, 64)
+# 'tc': tcgen05 tensor-core assignment (production path); 'simt': fp32 CUDA-core kernel kept for
+# cross-checking the two implementations against each other in the tests.
+DEFAULT_ASSIGN = os.environ.get("LEIDA_KMEANS_ASSIGN", "tc")
 
 
 def _bucket(k):
@@ -56,13 +60,27 @@ class KMeansEngine:
         nv.call("leida_kmeans_row_norms", nv.ptr(X), self.M, N, xp, nv.ptr(self.xnorm), nv.stream())
 
     # ------------------------------------------------------------------------------------------
-    def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1, profile=None):
+    def _tc_operands(self):
+        """bf16 x 2 split of the rows for the tensor-core path (made once per data set)."""
+        if getattr(self, "_x12", None) is None:
+            torch = self.torch
+            npk = int(nv.lib.leida_kmeans_tc_pitch(self.N))
+            x1 = torch.empty((self.M, npk), dtype=torch.bfloat16, device=self.X.device)
+            x2 = torch.empty((self.M, npk), dtype=torch.bfloat16, device=self.X.device)
+            nv.call("leida_kmeans_tc_split_rows", nv.ptr(self.X), self.M, self.N, self.XP, nv.ptr(x1), nv.ptr(x2), nv.stream())
+            self._x12 = (x1, x2, npk)
+        return self._x12
+
+    def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1, profile=None, assign=None):
         """runs: list of (k, init_rows) with init_rows = k global row indices.  Returns BatchResult.
         profile: optional list; (start, stop) CUDA event pairs bracketing every assign-kernel launch
         are appended to it (bench.py's live roofline measurement)."""
         torch = self.torch
         if centroid_update not in ("exact", "reference"):
             raise ValueError("centroid_update must be 'exact' or 'reference'")
+        assign = assign or DEFAULT_ASSIGN
+        if assign not in ("tc", "simt"):
+            raise ValueError("assign must be 'tc' (tensor cores) or 'simt'")
         if centroid_update == "reference" and self.comm.world > 1:
             raise ValueError("centroid_update='reference' (sequential float32 sums) cannot be sharded over GPUs")
         if self.M < 1:
@@ -109,16 +127,64 @@ class KMeansEngine:
                     self.N, self.XP, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), self.M, nv.ptr(state), st)
             acc_red, state_red = acc, state
 
+        if assign == "tc":
+            x1, x2, npk = self._tc_operands()
+            c_rows = (2 * CR + 128 + 127) // 128 * 128
+            c1 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
+            c2 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
+            labels_new = torch.empty((R, self.M), dtype=torch.int32, device=dev)
+            plan = torch.zeros(2, dtype=torch.int32, device=dev)
+            tile_first = torch.zeros(c_rows // 128, dtype=torch.int32, device=dev)
+            tile_count = torch.zeros(c_rows // 128, dtype=torch.int32, device=dev)
+            prun = torch.zeros(R, dtype=torch.int32, device=dev)
+            pcol = torch.zeros(R, dtype=torch.int32, device=dev)
+            run_pcol = torch.zeros(R, dtype=torch.int32, device=dev)
+
+            def tc_plan():
+                nv.call("leida_kmeans_tc_plan", R, nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm),
+                        self.N, self.XP, nv.ptr(plan), nv.ptr(tile_first), nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol),
+                        nv.ptr(run_pcol), nv.ptr(c1), nv.ptr(c2), st)
+
+            def tc_pass():
+                if profile is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                nv.call("leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
+                        self.N, nv.ptr(c1), nv.ptr(c2), c_rows, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(plan), nv.ptr(tile_first),
+                        nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels_new),
+                        nv.ptr(state), nv.ptr(worklist), cap, st)
+                if profile is not None:
+                    e1.record()
+                    profile.append((e0, e1))
+                nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, nv.ptr(run_k),
+                        nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
+                        nv.ptr(worklist), cap, nv.ptr(labels_new), st)
+                nv.call("leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_c0), nv.ptr(labels),
+                        nv.ptr(labels_new), nv.ptr(acc), nv.ptr(state), st)
+
+            tc_plan()
         # groups of consecutive (K-sorted) runs sharing a register tile
         groups, g0 = [], 0
         for i in range(1, R + 1):
             if i == R or _bucket(int(ks[i])) != _bucket(int(ks[g0])):
                 groups.append((g0, i, int(ks[g0:i].max())))
                 g0 = i
+        # Lock-step passes.  The host never blocks on the GPU inside the loop: after every pass the
+        # active-run count is copied to a pinned ring slot and the host looks only at slots whose
+        # copy has already completed, so it runs a few passes ahead (passes issued after every run
+        # has stopped are no-ops: inactive runs exit at once and leida_kmeans_update ignores them).
+        ring = 8
+        flags = torch.empty(ring, dtype=torch.int32, pin_memory=True)
+        flags.fill_(1)
+        events = [None] * ring
         passes = 0
         launches = 0
-        while True:
-            for (a, b, kmax) in groups:
+        done = False
+        while not done:
+            if assign == "tc":
+                tc_pass()
+                launches += 3
+            for (a, b, kmax) in (groups if assign == "simt" else ()):
                 if profile is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
@@ -132,7 +198,7 @@ class KMeansEngine:
                 nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
-                        nv.ptr(worklist), cap, st)
+                        nv.ptr(worklist), cap, None, st)
                 launches += 2
             if self.comm.world > 1:
                 acc_red.copy_(acc)
@@ -146,11 +212,23 @@ class KMeansEngine:
                 nv.call("leida_kmeans_means_f32_sequential", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_k),
                         nv.ptr(run_c0), nv.ptr(labels), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm), st)
                 launches += 2
+            if assign == "tc":
+                tc_plan()
+                launches += 2
+            slot = passes % ring
+            if events[slot] is not None:
+                events[slot].synchronize()            # ring full: wait for the oldest copy only
+                if int(flags[slot]) == 0:
+                    done = True
+            flags[slot:slot + 1].copy_(n_active, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            events[slot] = ev
             passes += 1
-            if passes % poll_every == 0 or passes > n_iter:
-                if int(n_active.item()) == 0:
-                    break
-            if passes > n_iter + 2:
+            for i in range(ring):
+                if events[i] is not None and events[i].query() and int(flags[i]) == 0:
+                    done = True
+            if passes > n_iter + 2 + ring:
                 raise nv.LeidaCudaError("k-means did not terminate (internal error)")
         nv.call("leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
                 nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), st)
@@ -173,8 +251,12 @@ class KMeansEngine:
         inertia[empty > 0] = np.nan
         inv = np.empty(R, dtype=np.int64)
         inv[np.asarray(order)] = np.arange(R)
-        return BatchResult(self, inv, ks, crow0, cent, labels, inertia, st_host[:, nv.ST_PASSES].copy(), empty, counts,
-                           launches, passes)
+        out = BatchResult(self, inv, ks, crow0, cent, labels, inertia, st_host[:, nv.ST_PASSES].copy(), empty, counts,
+                          launches, passes)
+        out.rechecked_total = int(st_host[:, nv.ST_RECHECK_TOTAL].sum())
+        out.changed_total = int(st_host[:, nv.ST_CHANGED_TOTAL].sum())
+        out.assign = assign
+        return out
 
     def predict(self, centers):
         """argmin cosine distance to `centers` (K, N) for every local row -> CUDA int32 (M,)."""
