@@ -197,7 +197,8 @@ int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64
                            const int32_t* prun, const int32_t* pcol, const int32_t* run_k, const int32_t* run_crow0,
                            int32_t* labels_new, int64_t* state, int32_t* worklist, int64_t worklist_cap,
                            leida_stream_t stream);
-int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs, const int32_t* run_crow0,
+int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs, int kmax,
+                          const int32_t* run_k, const int32_t* run_crow0,
                           int32_t* labels_cur, const int32_t* labels_new, int64_t* acc, int64_t* state,
                           leida_stream_t stream);
 

@@ -653,7 +653,7 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
     p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out;
-    k_recheck<<<sm_count() * 4, 128, 0, (cudaStream_t)stream>>>(p);
+    k_recheck<<<sm_count() * 8, 128, 0, (cudaStream_t)stream>>>(p);
     return check_launch("k_recheck");
 }
 

@@ -285,36 +285,70 @@ __global__ void k_split_rows(const float* __restrict__ X, long long M, int N, lo
     X2[i] = lo;
 }
 
-// Packing plan: active runs, in run order, placed side by side so that no run straddles a BN-column tile.
-__global__ void k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restrict__ state,
-                       int32_t* plan, int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol,
-                       int32_t* run_pcol) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int tile = 0, col = 0, np = 0, first = 0;
-    for (int r = 0; r < n_runs; ++r) {
-        run_pcol[r] = -1;
-        if (state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) continue;
-        const int K = run_k[r];
-        if (col + K > BN) {
-            tile_first[tile] = first;
-            tile_count[tile] = np - first;
-            ++tile;
-            col = 0;
-            first = np;
+// Packing plan: active runs, in run order, placed side by side so that no run straddles a BN-column
+// tile.  One CTA: the run table is staged in shared memory with coalesced loads, one thread does the
+// (inherently sequential, ~10 cycles per run) placement, all threads write the result back.
+constexpr int PLAN_MAX_RUNS = 4096;
+__global__ void __launch_bounds__(256)
+k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restrict__ state, int32_t* plan,
+       int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol, int32_t* run_pcol) {
+    __shared__ short s_k[PLAN_MAX_RUNS];        // K, or 0 when the run is not active
+    __shared__ int s_pc[PLAN_MAX_RUNS];         // packed global column or -1
+    __shared__ int s_tiles, s_np;
+    for (int r = threadIdx.x; r < n_runs; r += blockDim.x)
+        s_k[r] = state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] != 0 ? (short)run_k[r] : (short)0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tile = 0, col = 0, np = 0;
+        for (int r = 0; r < n_runs; ++r) {
+            const int K = s_k[r];
+            int pc = -1;
+            if (K > 0) {
+                if (col + K > BN) { ++tile; col = 0; }
+                pc = tile * BN + col;
+                col += K;
+                ++np;
+            }
+            s_pc[r] = pc;
         }
-        prun[np] = r;
-        pcol[np] = col;
-        run_pcol[r] = tile * BN + col;
-        col += K;
-        ++np;
+        s_tiles = np > 0 ? tile + 1 : 0;
+        s_np = np;
     }
-    if (np > first) {
-        tile_first[tile] = first;
-        tile_count[tile] = np - first;
-        ++tile;
+    __syncthreads();
+    const int n_tiles = s_tiles;
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) tile_count[t] = 0;
+    __syncthreads();
+    // packed index of run r = number of active runs before it: recomputed per thread chunk by a
+    // second pass of thread 0 would be serial again; instead every active run finds its rank with a
+    // block-wide inclusive scan over 256-run chunks.
+    __shared__ int s_scan[256];
+    int base = 0;
+    for (int r0 = 0; r0 < n_runs; r0 += 256) {
+        const int r = r0 + threadIdx.x;
+        const int a = (r < n_runs && s_k[r] > 0) ? 1 : 0;
+        s_scan[threadIdx.x] = a;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (r < n_runs) {
+            run_pcol[r] = s_pc[r];
+            if (a) {
+                const int idx = base + s_scan[threadIdx.x] - 1;
+                const int t = s_pc[r] / BN;
+                prun[idx] = r;
+                pcol[idx] = s_pc[r] - t * BN;
+                atomicAdd(&tile_count[t], 1);
+                if (s_pc[r] == t * BN) tile_first[t] = idx;       // the run that opens the tile
+            }
+        }
+        base += s_scan[255];
+        __syncthreads();
     }
-    plan[0] = tile;
-    plan[1] = np;
+    if (threadIdx.x == 0) { plan[0] = n_tiles; plan[1] = s_np; }
 }
 
 // Unit-normalised, bf16-split centroid rows of the active runs at their packed position.
@@ -343,43 +377,83 @@ __global__ void k_pack_centroids(const int32_t* __restrict__ run_k, const int32_
 
 // labels_cur vs labels_new of the active runs: count the changes, move the fixed-point row
 // contributions between clusters, and make the new labels current.
-__global__ void __launch_bounds__(256)
-k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ run_crow0,
-             int32_t* __restrict__ labels_cur, const int32_t* __restrict__ labels_new, long long* acc, long long* state) {
+// One CTA = (chunk of APPLY_ROWS rows, run).  The moves of the chunk are first summed in shared
+// memory -- thread j owns column j of every cluster, so plain loads/stores suffice -- and only the
+// per-cluster column sums that are non-zero reach global memory (K*N atomics per CTA at most instead
+// of 2*N per changed row).  Integer sums: any grouping gives the same result.
+constexpr int APPLY_ROWS = 1024;
+constexpr int APPLY_THREADS = 256;
+
+template <bool USE_SMEM>
+__global__ void __launch_bounds__(APPLY_THREADS)
+k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ run_k,
+             const int32_t* __restrict__ run_crow0, int32_t* __restrict__ labels_cur,
+             const int32_t* __restrict__ labels_new, long long* acc, long long* state) {
     const int run = blockIdx.y;
     if (state[(long long)run * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int crow0 = run_crow0[run];
+    extern __shared__ __align__(16) unsigned char sm_apply[];
+    int* s_list = reinterpret_cast<int*>(sm_apply);                       // [APPLY_ROWS] local row | old<<16 | new<<24
+    int* s_cnt = s_list + APPLY_ROWS;                                     // [64] count deltas
+    long long* S = reinterpret_cast<long long*>(s_cnt + 64);              // [K][XP] (USE_SMEM only)
+    __shared__ int s_n;
+    const int K = run_k[run], crow0 = run_crow0[run];
     const int AP = XP + 8;
+    const long long row_base = (long long)blockIdx.x * APPLY_ROWS;
     int32_t* cur = labels_cur + (long long)run * M;
     const int32_t* nw = labels_new + (long long)run * M;
-    const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x - lane);   // first row of this warp
-    const long long row = row0 + lane;
-    int o = 0, n = 0;
-    if (row < M) { o = cur[row]; n = nw[row]; }
-    const bool changed = (row < M) && (o != n);
-    unsigned mask = __ballot_sync(0xffffffffu, changed);
-    if (mask == 0) return;
-    if (changed) cur[row] = n;
-    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(state + (long long)run * kStateWordsTc + LEIDA_KM_ST_CHANGED),
-                             (unsigned long long)__popc(mask));
-    while (mask) {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int ob = __shfl_sync(0xffffffffu, o, b), nb = __shfl_sync(0xffffffffu, n, b);
-        const float* xr = X + (row0 + b) * XP;
-        long long* an = acc + (long long)(crow0 + nb) * AP;
-        long long* ao = acc + (long long)(crow0 + (ob < 0 ? 0 : ob)) * AP;
-        for (int j = lane; j < N; j += 32) {
-            const long long qv = __double2ll_rn((double)xr[j] * 1099511627776.0);
-            atomicAdd(reinterpret_cast<unsigned long long*>(an + j), (unsigned long long)qv);
-            if (ob >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(ao + j), (unsigned long long)(-qv));
-        }
-        if (lane == 0) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(an + XP), 1ull);
-            if (ob >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(ao + XP), (unsigned long long)(-1ll));
+    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < APPLY_ROWS; r += APPLY_THREADS) {
+        const long long row = row_base + r;
+        if (row < M) {
+            const int o = cur[row], n = nw[row];
+            if (o != n) {
+                cur[row] = n;
+                s_list[atomicAdd(&s_n, 1)] = r | ((o & 0xff) << 16) | (n << 24);
+                atomicAdd(&s_cnt[n], 1);
+                if (o >= 0) atomicAdd(&s_cnt[o], -1);
+            }
         }
     }
+    __syncthreads();
+    const int nchg = s_n;
+    if (nchg == 0) return;
+    if (USE_SMEM) {
+        for (int i = threadIdx.x; i < K * XP; i += APPLY_THREADS) S[i] = 0;
+        __syncthreads();
+        for (int j = threadIdx.x; j < N; j += APPLY_THREADS) {
+            for (int e = 0; e < nchg; ++e) {
+                const int v = s_list[e];
+                const int o = (v >> 16) & 0xff, n = (v >> 24) & 0xff;
+                const long long qv = __double2ll_rn((double)X[(row_base + (v & 0xffff)) * XP + j] * 1099511627776.0);
+                S[n * XP + j] += qv;
+                if (o != 0xff) S[o * XP + j] -= qv;
+            }
+            for (int k = 0; k < K; ++k) {
+                const long long d = S[k * XP + j];
+                if (d != 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + k) * AP + j), (unsigned long long)d);
+            }
+        }
+    } else {
+        for (int e = 0; e < nchg; ++e) {
+            const int v = s_list[e];
+            const int o = (v >> 16) & 0xff, n = (v >> 24) & 0xff;
+            const float* xr = X + (row_base + (v & 0xffff)) * XP;
+            for (int j = threadIdx.x; j < N; j += APPLY_THREADS) {
+                const long long qv = __double2ll_rn((double)xr[j] * 1099511627776.0);
+                atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + n) * AP + j), (unsigned long long)qv);
+                if (o != 0xff)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + o) * AP + j), (unsigned long long)(-qv));
+            }
+        }
+    }
+    if (threadIdx.x < K && s_cnt[threadIdx.x] != 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + threadIdx.x) * AP + XP),
+                  (unsigned long long)(long long)s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(state + (long long)run * kStateWordsTc + LEIDA_KM_ST_CHANGED),
+                  (unsigned long long)nchg);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -439,7 +513,8 @@ extern "C" int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int3
                       run_pcol && C1 && C2, "null pointer");
     LEIDA_REQUIRE(n_runs >= 1 && N >= 1 && x_pitch >= N, "sizes");
     const int NPK = (int)leida_kmeans_tc_pitch(N);
-    k_plan<<<1, 32, 0, st>>>(n_runs, run_k, (const long long*)state, plan, tile_first, tile_count, prun, pcol, run_pcol);
+    LEIDA_REQUIRE(n_runs <= PLAN_MAX_RUNS, "n_runs <= 4096 per batch");
+    k_plan<<<1, 256, 0, st>>>(n_runs, run_k, (const long long*)state, plan, tile_first, tile_count, prun, pcol, run_pcol);
     k_pack_centroids<<<n_runs, 256, 0, st>>>(run_k, run_crow0, run_pcol, cent, cnorm, N, (int)x_pitch, (__nv_bfloat16*)C1,
                                              (__nv_bfloat16*)C2, NPK);
     return check_launch("leida_kmeans_tc_plan", 2);
@@ -480,13 +555,23 @@ extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const floa
     return check_launch("k_tc_assign");
 }
 
-extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs,
-                                     const int32_t* run_crow0, int32_t* labels_cur, const int32_t* labels_new,
-                                     int64_t* acc, int64_t* state, leida_stream_t stream) {
-    LEIDA_REQUIRE(X && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
+extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs, int kmax,
+                                     const int32_t* run_k, const int32_t* run_crow0, int32_t* labels_cur,
+                                     const int32_t* labels_new, int64_t* acc, int64_t* state, leida_stream_t stream) {
+    LEIDA_REQUIRE(X && run_k && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
     LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && n_runs >= 1 && n_runs <= 65535, "sizes");
-    dim3 grid((unsigned)((M + 255) / 256), (unsigned)n_runs);
-    k_diff_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, run_crow0, labels_cur, labels_new,
-                                                          (long long*)acc, (long long*)state);
+    LEIDA_REQUIRE(kmax >= 2 && kmax <= LEIDA_KM_MAX_K, "2 <= kmax <= 64");
+    dim3 grid((unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS), (unsigned)n_runs);
+    const size_t fixed = (size_t)(APPLY_ROWS + 64) * sizeof(int);
+    const size_t with_s = fixed + (size_t)kmax * x_pitch * sizeof(long long);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (with_s <= 100 * 1024) {
+        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_diff_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_s));
+        k_diff_apply<true><<<grid, APPLY_THREADS, with_s, st>>>(X, M, N, (int)x_pitch, run_k, run_crow0, labels_cur,
+                                                                labels_new, (long long*)acc, (long long*)state);
+    } else {
+        k_diff_apply<false><<<grid, APPLY_THREADS, fixed, st>>>(X, M, N, (int)x_pitch, run_k, run_crow0, labels_cur,
+                                                                 labels_new, (long long*)acc, (long long*)state);
+    }
     return check_launch("k_diff_apply");
 }

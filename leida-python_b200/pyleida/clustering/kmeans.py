@@ -108,7 +108,7 @@ class KMeansEngine:
         acc = torch.empty((CR, AP), dtype=torch.int64, device=dev)
         labels = torch.empty((R, self.M), dtype=torch.int32, device=dev)
         state = torch.empty((R, nv.STATE_WORDS), dtype=torch.int64, device=dev)
-        cap = int(min(max(self.M // 4, 1 << 16), 1 << 24))
+        cap = int(min(max(R * self.M // 8, 1 << 16), 1 << 24))    # (run,row) pairs queued for the fp64 re-check per pass
         worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
         worklist[:8].zero_()
         n_active = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -127,6 +127,16 @@ class KMeansEngine:
                     self.N, self.XP, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), self.M, nv.ptr(state), st)
             acc_red, state_red = acc, state
 
+        def timed(name, fn):
+            want = profile is not None and (name == "assign" or isinstance(profile, dict))
+            if not want:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            (profile.setdefault(name, []) if isinstance(profile, dict) else profile).append((e0, e1))
+
         if assign == "tc":
             x1, x2, npk = self._tc_operands()
             c_rows = (2 * CR + 128 + 127) // 128 * 128
@@ -141,26 +151,26 @@ class KMeansEngine:
             run_pcol = torch.zeros(R, dtype=torch.int32, device=dev)
 
             def tc_plan():
+                timed("plan", _tc_plan)
+
+            def _tc_plan():
                 nv.call("leida_kmeans_tc_plan", R, nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm),
                         self.N, self.XP, nv.ptr(plan), nv.ptr(tile_first), nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol),
                         nv.ptr(run_pcol), nv.ptr(c1), nv.ptr(c2), st)
 
             def tc_pass():
-                if profile is not None:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                nv.call("leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
-                        self.N, nv.ptr(c1), nv.ptr(c2), c_rows, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(plan), nv.ptr(tile_first),
-                        nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels_new),
-                        nv.ptr(state), nv.ptr(worklist), cap, st)
-                if profile is not None:
-                    e1.record()
-                    profile.append((e0, e1))
-                nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, nv.ptr(run_k),
-                        nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
-                        nv.ptr(worklist), cap, nv.ptr(labels_new), st)
-                nv.call("leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_c0), nv.ptr(labels),
-                        nv.ptr(labels_new), nv.ptr(acc), nv.ptr(state), st)
+                timed("assign", lambda: nv.call(
+                    "leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
+                    self.N, nv.ptr(c1), nv.ptr(c2), c_rows, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(plan), nv.ptr(tile_first),
+                    nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels_new),
+                    nv.ptr(state), nv.ptr(worklist), cap, st))
+                timed("recheck", lambda: nv.call(
+                    "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, nv.ptr(run_k),
+                    nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
+                    nv.ptr(worklist), cap, nv.ptr(labels_new), st))
+                timed("apply", lambda: nv.call(
+                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, R, int(ks.max()), nv.ptr(run_k),
+                    nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc), nv.ptr(state), st))
 
             tc_plan()
         # groups of consecutive (K-sorted) runs sharing a register tile
@@ -205,8 +215,9 @@ class KMeansEngine:
                 state_red.copy_(state)
                 self.comm.all_reduce_sum_(acc_red)
                 self.comm.all_reduce_sum_(state_red)
-            nv.call("leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
-                    nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active), st)
+            timed("update", lambda: nv.call(
+                "leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
+                nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active), st))
             launches += 1
             if centroid_update == "reference":
                 nv.call("leida_kmeans_means_f32_sequential", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_k),

@@ -25,7 +25,7 @@ for rep in range(3):
     t2 = sync()
     runs, plan = sweep_runs(M, 2, 20, 15, None, inits)
     t3 = sync()
-    prof = []
+    prof = {}
     l0 = nv.launch_count()
     res = eng.run(runs, profile=prof if rep == 2 else None)
     t4 = sync()
@@ -35,8 +35,9 @@ for rep in range(3):
           f"kmeans run {1e3*(t4-t3):.2f} (launches {nv.launch_count()-l0}, lockstep {res.lockstep_passes}, run-passes {res.total_passes()}) | select {1e3*(t5-t4):.2f}")
     print(f"  assign={res.assign} rechecked {res.rechecked_total} of {res.total_passes() * M} row-passes "
           f"({res.rechecked_total / (res.total_passes() * M):.2e}), label changes {res.changed_total}")
-    if prof:
-        print("  assign events total ms:", sum(a.elapsed_time(b) for a, b in prof), "n", len(prof))
+    for name, evs in prof.items():
+        t = [a.elapsed_time(b) for a, b in evs]
+        print(f"  {name:8s} total {sum(t):8.2f} ms  n={len(t)}  first {t[0]:.3f}  median {np.median(t):.3f}  max {max(t):.3f}")
 # active runs per pass histogram
 p = np.sort(res._passes)
 print("passes per run: min/median/mean/max", p.min(), np.median(p), p.mean(), p.max())
