@@ -225,13 +225,21 @@ __global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
     if (tid == 0 && nchg > 0) atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_CHANGED, nchg);
 }
 
-// fp64 re-evaluation of the rows the fp32 pass could not decide.  One warp per entry.
+// fp64 re-evaluation of the rows the fast pass could not decide.  One warp per (run,row) entry:
+// the row is held in registers as doubles (lanes stride the columns), every centroid's dot product
+// is an fp64 FMA chain per lane plus a fixed-order butterfly sum, then the reference's formula
+// 1 - dot/(|x||c|) with clipping, first minimum wins.  (scipy's own build sums the dot product in two
+// SIMD lanes, so no particular fp64 summation order is "the" reference; any fp64 order agrees with it
+// to ~1e-16 and decides identically unless two distances coincide to that level.)
+constexpr int RECHECK_MAX_COLS_PER_LANE = 8;   // rows up to 256 columns stay in registers
+
 __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     long long count = p.worklist[0];
     if (count > p.worklist_cap) count = p.worklist_cap;
+    const bool in_regs = p.N <= 32 * RECHECK_MAX_COLS_PER_LANE;
     for (long long e = warp; e < count; e += nwarps) {
         const int run = p.worklist[8 + 2 * e];
         const long long row = p.worklist[8 + 2 * e + 1];
@@ -239,19 +247,34 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
         const int crow0 = p.run_crow0[run];
         const float* xr = p.X + row * p.XP;
         const double xn = p.xnorm[row];
+        double xv[RECHECK_MAX_COLS_PER_LANE];
+        if (in_regs) {
+#pragma unroll
+            for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) {
+                const int j = lane + 32 * i;
+                xv[i] = j < p.N ? (double)xr[j] : 0.0;
+            }
+        }
         double bd = INFINITY;
-        int bk = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
-            const double d = cosine_distance(dot_seq(xr, p.cent + (long long)(crow0 + k) * p.XP, p.N), xn, p.cnorm[crow0 + k]);
+        int bk = 0;
+        bool any_nan = false;
+        for (int k = 0; k < K; ++k) {
+            const float* cr = p.cent + (long long)(crow0 + k) * p.XP;
+            double s = 0.0;
+            if (in_regs) {
+#pragma unroll
+                for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) {
+                    const int j = lane + 32 * i;
+                    if (j < p.N) s = fma(xv[i], (double)cr[j], s);
+                }
+            } else {
+                for (int j = lane; j < p.N; j += 32) s = fma((double)xr[j], (double)cr[j], s);
+            }
+            s = warp_sum(s);
+            const double d = cosine_distance(s, xn, p.cnorm[crow0 + k]);
+            if (d != d && !any_nan) { any_nan = true; bd = -INFINITY; bk = k; }   // numpy argmin: first NaN wins
             if (d < bd) { bd = d; bk = k; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
-        }
-        if (bk == 0x7fffffff) bk = 0;   // every distance NaN: numpy's argmin returns the first index
         if (p.labels_out) {
             if (lane == 0) {
                 p.labels_out[(long long)run * p.M + row] = bk;

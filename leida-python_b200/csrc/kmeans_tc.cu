@@ -22,9 +22,10 @@ constexpr int kStateWordsTc = LEIDA_KM_STATE_WORDS;
 constexpr int BM = 128;          // rows per tile  (UMMA M)
 constexpr int BN = 128;          // packed centroid columns per tile (UMMA N)
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int ST = 2;            // smem pipeline stages
+constexpr int ST = 3;            // smem pipeline stages
 constexpr int STAGE_BYTES = 4 * BM * BK * 2;          // X1, X2, C1, C2 blocks: 64 KB
-constexpr int SCORE_PITCH = BN + 1;                   // floats; odd pitch: row-per-thread access is conflict free
+constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 256;                        // two fp32 accumulators of BN columns
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
@@ -73,23 +74,104 @@ __device__ __forceinline__ uint64_t umma_desc(const void* tile) {
     const uint64_t addr = (uint64_t)(smem_u32(tile) & 0x3FFFF) >> 4;
     return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int W> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r);
+template <> __device__ __forceinline__ void tmem_ld<4>(uint32_t t, uint32_t* r) { tmem_ld_x4(t, r); }
+template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t t, uint32_t* r) { tmem_ld_x8(t, r); }
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t t, uint32_t* r) { tmem_ld_x16(t, r); }
+template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t t, uint32_t* r) { tmem_ld_x32(t, r); }
+template <> __device__ __forceinline__ void tmem_ld<64>(uint32_t t, uint32_t* r) { tmem_ld_x64(t, r); }
+template <> __device__ __forceinline__ void tmem_ld<0>(uint32_t, uint32_t*) {}
+
+// Width (power-of-two pieces W1 + W2) of the TMEM read that covers a run of K columns.
+__host__ __device__ __forceinline__ int read_width(int K) {
+    return K <= 4 ? 4 : K <= 8 ? 8 : K <= 12 ? 12 : K <= 16 ? 16 : K <= 20 ? 20 : K <= 24 ? 24 : K <= 32 ? 32 : K <= 40 ? 40
+         : K <= 48 ? 48 : 64;
+}
+
+// Top-2 of a run's K scores read directly from TMEM.  The cluster index is packed into the 6 low
+// mantissa bits of each score (a 2^-17 relative perturbation, covered by the error bound), which
+// makes every key unique: best = max tree, second = max tree over the keys != best.  All trees are
+// fully unrolled over the read width, so the work is instruction-level parallel, not a chain.
+template <int W1, int W2>
+__device__ __forceinline__ void run_top2(uint32_t taddr, int K, float& best, float& second, int& bk) {
+    constexpr int W = W1 + W2;
+    uint32_t r[W];
+    tmem_ld<W1>(taddr, r);
+    tmem_ld<W2>(taddr + W1, r + W1);
+    tmem_ld_wait();
+    float key[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+        key[k] = k < K ? __uint_as_float((r[k] & 0xFFFFFFC0u) | (uint32_t)k) : -INFINITY;
+    float m[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) m[k] = key[k];
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1)
+#pragma unroll
+        for (int k = 0; k + o < W; k += 2 * o) m[k] = fmaxf(m[k], m[k + o]);
+    const float b = m[0];
+#pragma unroll
+    for (int k = 0; k < W; ++k) m[k] = (key[k] == b) ? -INFINITY : key[k];
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1)
+#pragma unroll
+        for (int k = 0; k + o < W; k += 2 * o) m[k] = fmaxf(m[k], m[k + o]);
+    bk = (int)(__float_as_uint(b) & 63u);
+    best = __uint_as_float(__float_as_uint(b) & 0xFFFFFFC0u);
+    second = __uint_as_float(__float_as_uint(m[0]) & 0xFFFFFFC0u);
+}
+
+__device__ __forceinline__ void run_top2_any(uint32_t taddr, int K, float& best, float& second, int& bk) {
+    switch (read_width(K)) {
+        case 4: run_top2<4, 0>(taddr, K, best, second, bk); break;
+        case 8: run_top2<8, 0>(taddr, K, best, second, bk); break;
+        case 12: run_top2<8, 4>(taddr, K, best, second, bk); break;
+        case 16: run_top2<16, 0>(taddr, K, best, second, bk); break;
+        case 20: run_top2<16, 4>(taddr, K, best, second, bk); break;
+        case 24: run_top2<16, 8>(taddr, K, best, second, bk); break;
+        case 32: run_top2<32, 0>(taddr, K, best, second, bk); break;
+        case 40: run_top2<32, 8>(taddr, K, best, second, bk); break;
+        case 48: run_top2<32, 16>(taddr, K, best, second, bk); break;
+        default: run_top2<64, 0>(taddr, K, best, second, bk); break;
+    }
+}
+
+// Rare path, kept out of line: queue the (run,row) pair for the fp64 re-check, or resolve it here
+// (serially, exactly) when the queue is full.  Returns the label to store (-2 = queued).
+struct TcParams;
+__device__ __noinline__ int defer_row(const TcParams& p, int run, long long row, int K);
 
 // Packing plan written by k_plan (device), read by the assign kernel.
 //   plan[0] = number of column tiles, plan[1] = number of packed (active) runs
 //   tile_first[t], tile_count[t] : slice of the packed run list that lives in tile t
-//   prun[i] = run id, pcol[i] = first column of the run inside its tile
+//   prun[i] = run id, pcol[i] = (first column of the run inside its tile) | (K << 8)
 struct TcParams {
     long long M;
     int nkb;   // k-blocks = NPK / 64
@@ -114,14 +196,33 @@ struct TcParams {
     long long* state;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__device__ __noinline__ int defer_row(const TcParams& p, int run, long long row, int K) {
+    const int slot = atomicAdd(p.worklist, 1);
+    if (slot < p.worklist_cap) {
+        p.worklist[8 + 2 * (long long)slot] = run;
+        p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
+        return -2;
+    }
+    const int crow0 = p.run_crow0[run];
+    const float* xr = p.X + row * p.XP;
+    const double xnd = p.xnorm[row];
+    double bd = INFINITY;
+    int out = 0;
+    for (int k = 0; k < K; ++k) {
+        const double d = cosine_distance(dot_seq(xr, p.cent + (long long)(crow0 + k) * p.XP, p.N), xnd, p.cnorm[crow0 + k]);
+        if (d < bd) { bd = d; out = k; }
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.state + (long long)run * kStateWordsTc + LEIDA_KM_ST_RECHECKED), 1ull);
+    return out;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
             const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* stages = base;                                         // ST * 64 KB
-    float* scores = reinterpret_cast<float*>(base + ST * STAGE_BYTES);    // BM * SCORE_PITCH floats
-    uint64_t* bars = reinterpret_cast<uint64_t*>(scores + BM * SCORE_PITCH + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + ST * STAGE_BYTES);
     uint64_t* full = bars;            // [ST]
     uint64_t* empty = bars + ST;      // [ST]
     uint64_t* tfull = bars + 2 * ST;  // [2]
@@ -131,7 +232,7 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -192,68 +293,46 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
                 }
         }
     } else if (n_ct > 0) {
+        // Epilogue: EPI_WARPS warps, two per TMEM lane quarter; the two warps of a quarter take the
+        // even / odd runs of every column tile.
         const int q = warp & 3;                       // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;             // 0 or 1
         const int r_in_tile = q * 32 + lane;
-        float* my = scores + r_in_tile * SCORE_PITCH;
         int acc = 0;
         uint32_t aphase = 0;
         for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) {
             const long long row = (long long)rt * BM + r_in_tile;
             const bool valid = row < p.M;
             const float thr = valid ? p.tau * (float)p.xnorm[row] : 0.f;
+            int32_t* lab = p.labels_new + row;
             for (int ct = 0; ct < n_ct; ++ct) {
+                const int first = p.tile_first[ct], cnt = p.tile_count[ct];
                 mbar_wait(&tfull[acc], aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
-                    float v[32];
-                    tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) my[c * 32 + j] = v[j];
+                for (int i0 = half; i0 < cnt; i0 += 64) {
+                    const int mi = i0 + 2 * lane;
+                    const int mine = mi < cnt ? first + mi : first;
+                    const int m_run = p.prun[mine], m_col = p.pcol[mine];
+                    const int nb = min(32, (cnt - i0 + 1) >> 1);
+                    for (int b = 0; b < nb; ++b) {
+                        const int run = __shfl_sync(0xffffffffu, m_run, b);
+                        const int ck = __shfl_sync(0xffffffffu, m_col, b);
+                        const int c0 = ck & 0xff, K = ck >> 8;
+                        float best, second;
+                        int bk;
+                        run_top2_any(taddr + c0, K, best, second, bk);
+                        if (valid) {
+                            int out = bk;
+                            if (!((best - second) > thr)) out = defer_row(p, run, row, K);
+                            lab[(long long)run * p.M] = out;
+                        }
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);            // accumulator may be overwritten by the next tile
                 acc ^= 1;
                 if (acc == 0) aphase ^= 1;
-                const int first = p.tile_first[ct], cnt = p.tile_count[ct];
-                for (int i = first; i < first + cnt; ++i) {
-                    const int run = p.prun[i], c0 = p.pcol[i], K = p.run_k[run];
-                    float best = -INFINITY, second = -INFINITY;
-                    int bk = 0;
-                    for (int k = 0; k < K; ++k) {
-                        const float s = my[c0 + k];
-                        const bool gt = s > best;
-                        second = gt ? best : fmaxf(second, s);
-                        bk = gt ? k : bk;
-                        best = gt ? s : best;
-                    }
-                    if (valid) {
-                        int out = bk;
-                        if (!((best - second) > thr)) {
-                            out = -2;
-                            const int slot = atomicAdd(p.worklist, 1);
-                            if (slot < p.worklist_cap) {
-                                p.worklist[8 + 2 * (long long)slot] = run;
-                                p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
-                            } else {
-                                const int crow0 = p.run_crow0[run];
-                                const float* xr = p.X + row * p.XP;
-                                const double xnd = p.xnorm[row];
-                                double bd = INFINITY;
-                                out = 0;
-                                for (int k = 0; k < K; ++k) {
-                                    const double d = cosine_distance(
-                                        dot_seq(xr, p.cent + (long long)(crow0 + k) * p.XP, p.N), xnd, p.cnorm[crow0 + k]);
-                                    if (d < bd) { bd = d; out = k; }
-                                }
-                                atomicAdd(reinterpret_cast<unsigned long long*>(
-                                              p.state + (long long)run * kStateWordsTc + LEIDA_KM_ST_RECHECKED), 1ull);
-                            }
-                        }
-                        p.labels_new[(long long)run * p.M + row] = out;
-                    }
-                }
             }
         }
     }
@@ -304,7 +383,7 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
             const int K = s_k[r];
             int pc = -1;
             if (K > 0) {
-                if (col + K > BN) { ++tile; col = 0; }
+                if (col + read_width(K) > BN) { ++tile; col = 0; }   // the TMEM read of the run must stay inside the tile
                 pc = tile * BN + col;
                 col += K;
                 ++np;
@@ -340,7 +419,7 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
                 const int idx = base + s_scan[threadIdx.x] - 1;
                 const int t = s_pc[r] / BN;
                 prun[idx] = r;
-                pcol[idx] = s_pc[r] - t * BN;
+                pcol[idx] = (s_pc[r] - t * BN) | ((int)s_k[r] << 8);
                 atomicAdd(&tile_count[t], 1);
                 if (s_pc[r] == t * BN) tile_first[t] = idx;       // the run that opens the tile
             }
@@ -542,16 +621,17 @@ extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const floa
     p.prun = prun; p.pcol = pcol; p.run_k = run_k; p.xnorm = xnorm;
     // Error bound of a score (|x| units): dropped split terms 3*2^-18, normalisation of c 2^-22, fp32
     // accumulation of 3*NPK products in the tensor core (<= 2^-22 each, not assumed round-to-nearest);
-    // doubled for the difference of two scores, 25% slack.
-    p.tau = 2.5f * (3.0f * 3.8147e-6f + 2.4e-7f + 3.0f * (float)NPK * 2.3842e-7f);
+    // index packing in the epilogue truncates 6 mantissa bits (2^-17); doubled for the difference of
+    // two scores, 25% slack.
+    p.tau = 2.5f * (3.0f * 3.8147e-6f + 2.4e-7f + 7.63e-6f + 3.0f * (float)NPK * 2.3842e-7f);
     p.labels_new = labels_new; p.worklist = worklist; p.worklist_cap = worklist_cap;
     p.X = X; p.XP = (int)x_pitch; p.N = N; p.cent = cent; p.cnorm = cnorm; p.run_crow0 = run_crow0;
     p.state = (long long*)state;
-    const size_t smem = 1024 + (size_t)ST * STAGE_BYTES + (size_t)(BM * SCORE_PITCH + 4) * sizeof(float) + 16 * sizeof(uint64_t);
+    const size_t smem = 1024 + (size_t)ST * STAGE_BYTES + 32 * sizeof(uint64_t);
     LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_tc_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_rt = (int)((M + BM - 1) / BM);
     const int grid = n_rt < sm_count() ? n_rt : sm_count();
-    k_tc_assign<<<grid, 192, smem, st>>>(mx1, mx2, mc1, mc2, p);
+    k_tc_assign<<<grid, TC_THREADS, smem, st>>>(mx1, mx2, mc1, mc2, p);
     return check_launch("k_tc_assign");
 }
 
