@@ -267,7 +267,7 @@ def native_arm(args):
 
     for _ in range(args.warmup):
         step_device()
-    profile = {}
+    profile = {} if os.environ.get("LEIDA_BENCH_PROFILE_ALL") else {"assign": []}
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:

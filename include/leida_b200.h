@@ -189,7 +189,10 @@ int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch
 int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int32_t* run_crow0, const int64_t* state,
                          const float* cent, const double* cnorm, int N, int64_t x_pitch,
                          int32_t* plan, int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol,
-                         int32_t* run_pcol, void* C1, void* C2, leida_stream_t stream);
+                         int32_t* run_pcol, void* C1, void* C2, int pack, leida_stream_t stream);
+/* pack != 0 also writes C1/C2 from cent/cnorm (needed once after leida_kmeans_init; afterwards
+ * leida_kmeans_update keeps them current).  The plan may be refreshed at any pass boundary (before
+ * leida_kmeans_update); runs that stopped simply stay packed until the next refresh. */
 int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64_t x_pitch, const double* xnorm,
                            int64_t M, int N, const void* C1, const void* C2, int64_t c_rows,
                            const float* cent, const double* cnorm,
@@ -197,7 +200,8 @@ int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64
                            const int32_t* prun, const int32_t* pcol, const int32_t* run_k, const int32_t* run_crow0,
                            int32_t* labels_new, int64_t* state, int32_t* worklist, int64_t worklist_cap,
                            leida_stream_t stream);
-int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs, int kmax,
+int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs_bound,
+                          const int32_t* plan, const int32_t* prun,
                           const int32_t* run_k, const int32_t* run_crow0,
                           int32_t* labels_cur, const int32_t* labels_new, int64_t* acc, int64_t* state,
                           leida_stream_t stream);
@@ -210,7 +214,11 @@ int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int
 int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
                         const int64_t* acc_reduced, const int64_t* state_reduced,
                         float* cent, double* cnorm, int64_t* state, int n_iter,
-                        int32_t* n_active_out, leida_stream_t stream);
+                        int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
+                        leida_stream_t stream);
+/* run_pcol / C1 / C2 (all NULL in the SIMT flow): the tensor-core operands of every packed run --
+ * unit-normalised centroids split into bf16 hi/lo rows at the run's packed column -- are rewritten
+ * here, so the next leida_kmeans_tc_assign needs no separate packing launch. */
 
 /* Distortion of every run against its final centroids (clustering/_clustering.py:209-232), fp64
  * per row, accumulated as exact integers into state[DIST_HI/LO]. */

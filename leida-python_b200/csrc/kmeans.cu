@@ -11,6 +11,7 @@
 //   * centroid sums are int64 fixed point (2^40) and updated incrementally by the rows whose label
 //     changed: exact, order independent, identical for any number of GPUs.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace leida {
@@ -373,7 +374,8 @@ __global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
 __global__ void __launch_bounds__(256)
 k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int N, int XP,
          const long long* __restrict__ acc_red, const long long* __restrict__ state_red, float* cent, double* cnorm,
-         long long* state, int n_iter, int32_t* n_active) {
+         long long* state, int n_iter, int32_t* n_active, const int32_t* __restrict__ run_pcol,
+         __nv_bfloat16* __restrict__ C1, __nv_bfloat16* __restrict__ C2, int NPK) {
     const int run = blockIdx.x;
     long long* st = state + (long long)run * kStateWords;
     __shared__ int s_go;
@@ -409,22 +411,42 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
         if (go) atomicAdd(n_active, 1);
     }
     __syncthreads();
-    if (!s_go) return;
-    for (int i = threadIdx.x; i < K * XP; i += blockDim.x) {
-        const int k = i / XP, j = i - k * XP;
-        float v = 0.f;
-        if (j < N) {
-            const long long cnt = acc_red[(long long)(crow0 + k) * AP + XP];
-            const double sum = (double)acc_red[(long long)(crow0 + k) * AP + j] * (1.0 / kFracScale);
-            v = (float)(sum / (double)cnt);
+    const int pc = run_pcol ? run_pcol[run] : -1;
+    if (s_go) {
+        for (int i = threadIdx.x; i < K * XP; i += blockDim.x) {
+            const int k = i / XP, j = i - k * XP;
+            float v = 0.f;
+            if (j < N) {
+                const long long cnt = acc_red[(long long)(crow0 + k) * AP + XP];
+                const double sum = (double)acc_red[(long long)(crow0 + k) * AP + j] * (1.0 / kFracScale);
+                v = (float)(sum / (double)cnt);
+            }
+            cent[(long long)(crow0 + k) * XP + j] = v;
         }
-        cent[(long long)(crow0 + k) * XP + j] = v;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int k = w; k < K; k += nw) {
+            const double n = cent_norm_warp(cent + (long long)(crow0 + k) * XP, N, lane);
+            if (lane == 0) cnorm[crow0 + k] = n;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int k = w; k < K; k += nw) {
-        const double n = cent_norm_warp(cent + (long long)(crow0 + k) * XP, N, lane);
-        if (lane == 0) cnorm[crow0 + k] = n;
+    // tensor-core operands of this run at its packed position: unit-normalised centroids, bf16 hi/lo.
+    // Written for every packed run (also one that just stopped), so the packed matrix never holds
+    // stale rows of another run after a re-plan.
+    if (pc >= 0) {
+        for (int i = threadIdx.x; i < K * NPK; i += blockDim.x) {
+            const int k = i / NPK, j = i - k * NPK;
+            float v = 0.f;
+            if (j < N) {
+                const double cn = cnorm[crow0 + k];
+                const float inv = cn > 0.0 ? (float)(1.0 / cn) : 0.f;
+                v = cent[(long long)(crow0 + k) * XP + j] * inv;
+            }
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            C1[(long long)(pc + k) * NPK + j] = hi;
+            C2[(long long)(pc + k) * NPK + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
     }
 }
 
@@ -676,21 +698,25 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
     p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out;
-    k_recheck<<<sm_count() * 8, 128, 0, (cudaStream_t)stream>>>(p);
+    k_recheck<<<sm_count() * 4, 128, 0, (cudaStream_t)stream>>>(p);
     return check_launch("k_recheck");
 }
 
 extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
                                    const int64_t* acc_reduced, const int64_t* state_reduced, float* cent, double* cnorm,
-                                   int64_t* state, int n_iter, int32_t* n_active_out, leida_stream_t stream) {
+                                   int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol, void* C1,
+                                   void* C2, leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LEIDA_REQUIRE(run_k && run_crow0 && acc_reduced && state_reduced && cent && cnorm && state && n_active_out, "null pointer");
     int rc = check_runs(n_runs, N, x_pitch);
     if (rc) return rc;
     LEIDA_REQUIRE(n_iter >= 0, "n_iter >= 0");
     LEIDA_CUDA_TRY(cudaMemsetAsync(n_active_out, 0, sizeof(int32_t), st));
+    LEIDA_REQUIRE((run_pcol == nullptr) == (C1 == nullptr) && (C1 == nullptr) == (C2 == nullptr), "run_pcol, C1, C2 together");
+    const int NPK = (int)(((int64_t)N + 63) / 64 * 64);
     k_update<<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, (const long long*)acc_reduced,
-                                     (const long long*)state_reduced, cent, cnorm, (long long*)state, n_iter, n_active_out);
+                                     (const long long*)state_reduced, cent, cnorm, (long long*)state, n_iter, n_active_out,
+                                     run_pcol, (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK);
     return check_launch("k_update");
 }
 

@@ -454,26 +454,29 @@ __global__ void k_pack_centroids(const int32_t* __restrict__ run_k, const int32_
     }
 }
 
-// labels_cur vs labels_new of the active runs: count the changes, move the fixed-point row
+// labels_cur vs labels_new of the packed runs: count the changes, move the fixed-point row
 // contributions between clusters, and make the new labels current.
-// One CTA = (chunk of APPLY_ROWS rows, run).  The moves of the chunk are first summed in shared
-// memory -- thread j owns column j of every cluster, so plain loads/stores suffice -- and only the
-// per-cluster column sums that are non-zero reach global memory (K*N atomics per CTA at most instead
-// of 2*N per changed row).  Integer sums: any grouping gives the same result.
+// One CTA = (chunk of APPLY_ROWS rows, packed run).  The chunk's changes are counting-sorted by
+// cluster in shared memory; then thread (g, j) sums column j over its share of the rows entering
+// (leaving) cluster k in a REGISTER -- independent loads, no read-modify-write chain -- and issues one
+// global int64 atomic per (cluster, column) it touched.  Integer sums: any grouping gives the same result.
 constexpr int APPLY_ROWS = 1024;
 constexpr int APPLY_THREADS = 256;
 
-template <bool USE_SMEM>
+__device__ __forceinline__ long long quant40(float v) { return __double2ll_rn((double)v * 1099511627776.0); }
+
 __global__ void __launch_bounds__(APPLY_THREADS)
-k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ run_k,
+k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ plan,
+             const int32_t* __restrict__ prun, const int32_t* __restrict__ run_k,
              const int32_t* __restrict__ run_crow0, int32_t* __restrict__ labels_cur,
              const int32_t* __restrict__ labels_new, long long* acc, long long* state) {
-    const int run = blockIdx.y;
+    if ((int)blockIdx.y >= plan[1]) return;
+    const int run = prun[blockIdx.y];
     if (state[(long long)run * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) return;
-    extern __shared__ __align__(16) unsigned char sm_apply[];
-    int* s_list = reinterpret_cast<int*>(sm_apply);                       // [APPLY_ROWS] local row | old<<16 | new<<24
-    int* s_cnt = s_list + APPLY_ROWS;                                     // [64] count deltas
-    long long* S = reinterpret_cast<long long*>(s_cnt + 64);              // [K][XP] (USE_SMEM only)
+    __shared__ int s_list[APPLY_ROWS];       // local row | old<<16 | new<<24
+    __shared__ short s_in[APPLY_ROWS];       // local rows sorted by NEW cluster
+    __shared__ short s_out[APPLY_ROWS];      // local rows sorted by OLD cluster (old >= 0 only)
+    __shared__ int s_cin[LEIDA_KM_MAX_K + 1], s_cout[LEIDA_KM_MAX_K + 1], s_pin[LEIDA_KM_MAX_K], s_pout[LEIDA_KM_MAX_K];
     __shared__ int s_n;
     const int K = run_k[run], crow0 = run_crow0[run];
     const int AP = XP + 8;
@@ -481,7 +484,7 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     int32_t* cur = labels_cur + (long long)run * M;
     const int32_t* nw = labels_new + (long long)run * M;
     if (threadIdx.x == 0) s_n = 0;
-    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x <= LEIDA_KM_MAX_K) { s_cin[threadIdx.x] = 0; s_cout[threadIdx.x] = 0; }
     __syncthreads();
     for (int r = threadIdx.x; r < APPLY_ROWS; r += APPLY_THREADS) {
         const long long row = row_base + r;
@@ -490,46 +493,56 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
             if (o != n) {
                 cur[row] = n;
                 s_list[atomicAdd(&s_n, 1)] = r | ((o & 0xff) << 16) | (n << 24);
-                atomicAdd(&s_cnt[n], 1);
-                if (o >= 0) atomicAdd(&s_cnt[o], -1);
+                atomicAdd(&s_cin[n], 1);
+                if (o >= 0) atomicAdd(&s_cout[o], 1);
             }
         }
     }
     __syncthreads();
     const int nchg = s_n;
     if (nchg == 0) return;
-    if (USE_SMEM) {
-        for (int i = threadIdx.x; i < K * XP; i += APPLY_THREADS) S[i] = 0;
-        __syncthreads();
-        for (int j = threadIdx.x; j < N; j += APPLY_THREADS) {
-            for (int e = 0; e < nchg; ++e) {
-                const int v = s_list[e];
-                const int o = (v >> 16) & 0xff, n = (v >> 24) & 0xff;
-                const long long qv = __double2ll_rn((double)X[(row_base + (v & 0xffff)) * XP + j] * 1099511627776.0);
-                S[n * XP + j] += qv;
-                if (o != 0xff) S[o * XP + j] -= qv;
-            }
-            for (int k = 0; k < K; ++k) {
-                const long long d = S[k * XP + j];
-                if (d != 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + k) * AP + j), (unsigned long long)d);
-            }
+    if (threadIdx.x == 0) {          // exclusive prefix sums (K <= 64)
+        int a = 0, b = 0;
+        for (int k = 0; k < K; ++k) {
+            const int ci = s_cin[k], co = s_cout[k];
+            s_pin[k] = a; s_pout[k] = b;
+            s_cin[k] = a; s_cout[k] = b;
+            a += ci; b += co;
         }
-    } else {
-        for (int e = 0; e < nchg; ++e) {
-            const int v = s_list[e];
-            const int o = (v >> 16) & 0xff, n = (v >> 24) & 0xff;
-            const float* xr = X + (row_base + (v & 0xffff)) * XP;
-            for (int j = threadIdx.x; j < N; j += APPLY_THREADS) {
-                const long long qv = __double2ll_rn((double)xr[j] * 1099511627776.0);
-                atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + n) * AP + j), (unsigned long long)qv);
-                if (o != 0xff)
-                    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + o) * AP + j), (unsigned long long)(-qv));
+        s_cin[K] = a; s_cout[K] = b;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nchg; e += APPLY_THREADS) {
+        const int v = s_list[e];
+        const int o = (v >> 16) & 0xff, n = (v >> 24) & 0xff;
+        s_in[atomicAdd(&s_pin[n], 1)] = (short)(v & 0xffff);
+        if (o != 0xff) s_out[atomicAdd(&s_pout[o], 1)] = (short)(v & 0xffff);
+    }
+    __syncthreads();
+    const int CW = N >= APPLY_THREADS ? APPLY_THREADS : ((N + 31) & ~31);
+    const int groups = APPLY_THREADS / CW;
+    const int g = threadIdx.x / CW, j0 = threadIdx.x - g * CW;
+    if (g < groups) {
+        const float* xb = X + row_base * XP;
+        for (int k = 0; k < K; ++k) {
+            const int ib = s_cin[k], ie = s_cin[k + 1], ob = s_cout[k], oe = s_cout[k + 1];
+            if (ib == ie && ob == oe) continue;
+            for (int j = j0; j < N; j += CW) {
+                long long sum = 0;
+#pragma unroll 4
+                for (int e = ib + g; e < ie; e += groups) sum += quant40(xb[(long long)s_in[e] * XP + j]);
+#pragma unroll 4
+                for (int e = ob + g; e < oe; e += groups) sum -= quant40(xb[(long long)s_out[e] * XP + j]);
+                if (sum != 0)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + k) * AP + j), (unsigned long long)sum);
             }
         }
     }
-    if (threadIdx.x < K && s_cnt[threadIdx.x] != 0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + threadIdx.x) * AP + XP),
-                  (unsigned long long)(long long)s_cnt[threadIdx.x]);
+    if (threadIdx.x < K) {
+        const int d = (s_cin[threadIdx.x + 1] - s_cin[threadIdx.x]) - (s_cout[threadIdx.x + 1] - s_cout[threadIdx.x]);
+        if (d != 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + threadIdx.x) * AP + XP), (unsigned long long)(long long)d);
+    }
     if (threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(state + (long long)run * kStateWordsTc + LEIDA_KM_ST_CHANGED),
                   (unsigned long long)nchg);
@@ -586,17 +599,18 @@ extern "C" int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int6
 extern "C" int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int32_t* run_crow0, const int64_t* state,
                                     const float* cent, const double* cnorm, int N, int64_t x_pitch, int32_t* plan,
                                     int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol,
-                                    int32_t* run_pcol, void* C1, void* C2, leida_stream_t stream) {
+                                    int32_t* run_pcol, void* C1, void* C2, int pack, leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LEIDA_REQUIRE(run_k && run_crow0 && state && cent && cnorm && plan && tile_first && tile_count && prun && pcol &&
                       run_pcol && C1 && C2, "null pointer");
     LEIDA_REQUIRE(n_runs >= 1 && N >= 1 && x_pitch >= N, "sizes");
-    const int NPK = (int)leida_kmeans_tc_pitch(N);
     LEIDA_REQUIRE(n_runs <= PLAN_MAX_RUNS, "n_runs <= 4096 per batch");
+    const int NPK = (int)leida_kmeans_tc_pitch(N);
     k_plan<<<1, 256, 0, st>>>(n_runs, run_k, (const long long*)state, plan, tile_first, tile_count, prun, pcol, run_pcol);
-    k_pack_centroids<<<n_runs, 256, 0, st>>>(run_k, run_crow0, run_pcol, cent, cnorm, N, (int)x_pitch, (__nv_bfloat16*)C1,
-                                             (__nv_bfloat16*)C2, NPK);
-    return check_launch("leida_kmeans_tc_plan", 2);
+    if (pack)
+        k_pack_centroids<<<n_runs, 256, 0, st>>>(run_k, run_crow0, run_pcol, cent, cnorm, N, (int)x_pitch,
+                                                 (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK);
+    return check_launch("leida_kmeans_tc_plan", pack ? 2 : 1);
 }
 
 extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64_t x_pitch,
@@ -635,23 +649,15 @@ extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const floa
     return check_launch("k_tc_assign");
 }
 
-extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs, int kmax,
-                                     const int32_t* run_k, const int32_t* run_crow0, int32_t* labels_cur,
-                                     const int32_t* labels_new, int64_t* acc, int64_t* state, leida_stream_t stream) {
-    LEIDA_REQUIRE(X && run_k && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
-    LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && n_runs >= 1 && n_runs <= 65535, "sizes");
-    LEIDA_REQUIRE(kmax >= 2 && kmax <= LEIDA_KM_MAX_K, "2 <= kmax <= 64");
-    dim3 grid((unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS), (unsigned)n_runs);
-    const size_t fixed = (size_t)(APPLY_ROWS + 64) * sizeof(int);
-    const size_t with_s = fixed + (size_t)kmax * x_pitch * sizeof(long long);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (with_s <= 100 * 1024) {
-        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_diff_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_s));
-        k_diff_apply<true><<<grid, APPLY_THREADS, with_s, st>>>(X, M, N, (int)x_pitch, run_k, run_crow0, labels_cur,
-                                                                labels_new, (long long*)acc, (long long*)state);
-    } else {
-        k_diff_apply<false><<<grid, APPLY_THREADS, fixed, st>>>(X, M, N, (int)x_pitch, run_k, run_crow0, labels_cur,
-                                                                 labels_new, (long long*)acc, (long long*)state);
-    }
+extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs_bound,
+                                     const int32_t* plan, const int32_t* prun, const int32_t* run_k,
+                                     const int32_t* run_crow0, int32_t* labels_cur, const int32_t* labels_new,
+                                     int64_t* acc, int64_t* state, leida_stream_t stream) {
+    LEIDA_REQUIRE(X && plan && prun && run_k && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
+    LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && n_runs_bound >= 1 && n_runs_bound <= 65535, "sizes");
+    dim3 grid((unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS), (unsigned)n_runs_bound);
+    k_diff_apply<<<grid, APPLY_THREADS, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, plan, prun, run_k, run_crow0,
+                                                                   labels_cur, labels_new, (long long*)acc,
+                                                                   (long long*)state);
     return check_launch("k_diff_apply");
 }

@@ -128,7 +128,8 @@ class KMeansEngine:
             acc_red, state_red = acc, state
 
         def timed(name, fn):
-            want = profile is not None and (name == "assign" or isinstance(profile, dict))
+            want = profile is not None and (name in profile if isinstance(profile, dict) and profile else
+                                            name == "assign" or isinstance(profile, dict))
             if not want:
                 return fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -150,13 +151,11 @@ class KMeansEngine:
             pcol = torch.zeros(R, dtype=torch.int32, device=dev)
             run_pcol = torch.zeros(R, dtype=torch.int32, device=dev)
 
-            def tc_plan():
-                timed("plan", _tc_plan)
-
-            def _tc_plan():
-                nv.call("leida_kmeans_tc_plan", R, nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm),
-                        self.N, self.XP, nv.ptr(plan), nv.ptr(tile_first), nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol),
-                        nv.ptr(run_pcol), nv.ptr(c1), nv.ptr(c2), st)
+            def tc_plan(pack):
+                timed("plan", lambda: nv.call(
+                    "leida_kmeans_tc_plan", R, nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm),
+                    self.N, self.XP, nv.ptr(plan), nv.ptr(tile_first), nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol),
+                    nv.ptr(run_pcol), nv.ptr(c1), nv.ptr(c2), int(pack), st))
 
             def tc_pass():
                 timed("assign", lambda: nv.call(
@@ -169,10 +168,12 @@ class KMeansEngine:
                     nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
                     nv.ptr(worklist), cap, nv.ptr(labels_new), st))
                 timed("apply", lambda: nv.call(
-                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, R, int(ks.max()), nv.ptr(run_k),
-                    nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc), nv.ptr(state), st))
+                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(packed_bound[0]), nv.ptr(plan),
+                    nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
+                    nv.ptr(state), st))
 
-            tc_plan()
+            packed_bound = [R]          # host-side upper bound of the number of packed runs (plan[1] on the device)
+            tc_plan(True)
         # groups of consecutive (K-sorted) runs sharing a register tile
         groups, g0 = [], 0
         for i in range(1, R + 1):
@@ -180,31 +181,30 @@ class KMeansEngine:
                 groups.append((g0, i, int(ks[g0:i].max())))
                 g0 = i
         # Lock-step passes.  The host never blocks on the GPU inside the loop: after every pass the
-        # active-run count is copied to a pinned ring slot and the host looks only at slots whose
-        # copy has already completed, so it runs a few passes ahead (passes issued after every run
-        # has stopped are no-ops: inactive runs exit at once and leida_kmeans_update ignores them).
+        # active-run count is copied to a pinned ring slot and the host reads slots whose copy has
+        # completed, so it runs a few passes ahead (passes issued after every run has stopped are
+        # no-ops: stopped runs are skipped by every kernel).  The count is non-increasing, so a stale
+        # value is a valid upper bound: it sizes the apply grid and triggers re-packing of the
+        # tensor-core operands once enough runs have stopped.
         ring = 8
         flags = torch.empty(ring, dtype=torch.int32, pin_memory=True)
-        flags.fill_(1)
+        flags.fill_(R)
+        flags_np = flags.numpy()
         events = [None] * ring
         passes = 0
         launches = 0
+        active_bound = R
         done = False
         while not done:
             if assign == "tc":
                 tc_pass()
                 launches += 3
             for (a, b, kmax) in (groups if assign == "simt" else ()):
-                if profile is not None:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                nv.call("leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
-                        run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
-                        labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
-                        nv.ptr(worklist), cap, st)
-                if profile is not None:
-                    e1.record()
-                    profile.append((e0, e1))
+                timed("assign", lambda: nv.call(
+                    "leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
+                    run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
+                    labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
+                    nv.ptr(worklist), cap, st))
                 nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
@@ -215,30 +215,39 @@ class KMeansEngine:
                 state_red.copy_(state)
                 self.comm.all_reduce_sum_(acc_red)
                 self.comm.all_reduce_sum_(state_red)
+            if assign == "tc" and 0 < active_bound <= 0.8 * packed_bound[0]:
+                tc_plan(False)                       # uses the activity flags of the previous update
+                packed_bound[0] = active_bound
+                launches += 1
             timed("update", lambda: nv.call(
                 "leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
-                nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active), st))
+                nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
+                nv.ptr(run_pcol) if assign == "tc" else None, nv.ptr(c1) if assign == "tc" else None,
+                nv.ptr(c2) if assign == "tc" else None, st))
             launches += 1
             if centroid_update == "reference":
                 nv.call("leida_kmeans_means_f32_sequential", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_k),
                         nv.ptr(run_c0), nv.ptr(labels), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm), st)
                 launches += 2
-            if assign == "tc":
-                tc_plan()
-                launches += 2
+                if assign == "tc":
+                    tc_plan(True)                    # the float32 sequential means replace the centroids: re-pack
+                    launches += 2
             slot = passes % ring
             if events[slot] is not None:
-                events[slot].synchronize()            # ring full: wait for the oldest copy only
-                if int(flags[slot]) == 0:
-                    done = True
+                events[slot].synchronize()            # ring full: wait for the oldest copy only ...
+                active_bound = min(active_bound, int(flags_np[slot]))   # ... and use its value before the slot is reused
             flags[slot:slot + 1].copy_(n_active, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             events[slot] = ev
             passes += 1
-            for i in range(ring):
-                if events[i] is not None and events[i].query() and int(flags[i]) == 0:
-                    done = True
+            for i in range(ring):                     # newest completed count
+                j = (slot - i) % ring
+                if events[j] is not None and events[j].query():
+                    active_bound = min(active_bound, int(flags_np[j]))
+                    break
+            if active_bound == 0:
+                done = True
             if passes > n_iter + 2 + ring:
                 raise nv.LeidaCudaError("k-means did not terminate (internal error)")
         nv.call("leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
