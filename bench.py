@@ -267,7 +267,7 @@ def native_arm(args):
 
     for _ in range(args.warmup):
         step_device()
-    profile = {} if os.environ.get("LEIDA_BENCH_PROFILE_ALL") else {"assign": []}
+    profile = {"*": True} if os.environ.get("LEIDA_BENCH_PROFILE_ALL") else {"assign": []}
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -292,7 +292,7 @@ def native_arm(args):
     value = M_global * args.steps / (ms * 1e-3)
 
     # roofline of the dominant kernel, from the event pairs recorded inside the timed region
-    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in profile.items()}
+    kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in profile.items() if k != "*"}
     assign_ms = kernel_ms.get("assign", 0.0)
     n_assign = len(profile.get("assign", []))
     run_passes = last.batch.total_passes()             # per step (same every step: deterministic)

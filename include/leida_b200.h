@@ -215,7 +215,11 @@ int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_cro
                         const int64_t* acc_reduced, const int64_t* state_reduced,
                         float* cent, double* cnorm, int64_t* state, int n_iter,
                         int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
-                        leida_stream_t stream);
+                        int32_t* mailbox, leida_stream_t stream);
+/* n_active_out: device int32[4], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
+ * [2] = runs still active after this call).  mailbox (may be NULL): HOST-visible (pinned, mapped)
+ * int32[2]; the last CTA stores {runs still active, number of update calls completed} there so the
+ * host can follow convergence without synchronising or copying. */
 /* run_pcol / C1 / C2 (all NULL in the SIMT flow): the tensor-core operands of every packed run --
  * unit-normalised centroids split into bf16 hi/lo rows at the run's packed column -- are rewritten
  * here, so the next leida_kmeans_tc_assign needs no separate packing launch. */

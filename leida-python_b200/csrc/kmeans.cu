@@ -259,22 +259,40 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
         double bd = INFINITY;
         int bk = 0;
         bool any_nan = false;
-        for (int k = 0; k < K; ++k) {
-            const float* cr = p.cent + (long long)(crow0 + k) * p.XP;
-            double s = 0.0;
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
             if (in_regs) {
+                float cv[4][RECHECK_MAX_COLS_PER_LANE];
 #pragma unroll
-                for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) {
-                    const int j = lane + 32 * i;
-                    if (j < p.N) s = fma(xv[i], (double)cr[j], s);
+                for (int u = 0; u < 4; ++u) {
+                    const float* cr = p.cent + (long long)(crow0 + min(k0 + u, K - 1)) * p.XP;
+#pragma unroll
+                    for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) {
+                        const int j = lane + 32 * i;
+                        cv[u][i] = j < p.N ? cr[j] : 0.f;
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) s4[u] = fma(xv[i], (double)cv[u][i], s4[u]);
             } else {
-                for (int j = lane; j < p.N; j += 32) s = fma((double)xr[j], (double)cr[j], s);
+                for (int u = 0; u < 4; ++u) {
+                    const float* cr = p.cent + (long long)(crow0 + min(k0 + u, K - 1)) * p.XP;
+                    for (int j = lane; j < p.N; j += 32) s4[u] = fma((double)xr[j], (double)cr[j], s4[u]);
+                }
             }
-            s = warp_sum(s);
-            const double d = cosine_distance(s, xn, p.cnorm[crow0 + k]);
-            if (d != d && !any_nan) { any_nan = true; bd = -INFINITY; bk = k; }   // numpy argmin: first NaN wins
-            if (d < bd) { bd = d; bk = k; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s4[u] = warp_sum(s4[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u;
+                if (k < K) {
+                    const double d = cosine_distance(s4[u], xn, p.cnorm[crow0 + k]);
+                    if (d != d && !any_nan) { any_nan = true; bd = -INFINITY; bk = k; }   // numpy argmin: first NaN wins
+                    if (d < bd) { bd = d; bk = k; }
+                }
+            }
         }
         if (p.labels_out) {
             if (lane == 0) {
@@ -375,13 +393,17 @@ __global__ void __launch_bounds__(256)
 k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int N, int XP,
          const long long* __restrict__ acc_red, const long long* __restrict__ state_red, float* cent, double* cnorm,
          long long* state, int n_iter, int32_t* n_active, const int32_t* __restrict__ run_pcol,
-         __nv_bfloat16* __restrict__ C1, __nv_bfloat16* __restrict__ C2, int NPK) {
+         __nv_bfloat16* __restrict__ C1, __nv_bfloat16* __restrict__ C2, int NPK, volatile int32_t* mailbox) {
     const int run = blockIdx.x;
     long long* st = state + (long long)run * kStateWords;
     __shared__ int s_go;
     __shared__ int s_empty;
     const int K = run_k[run], crow0 = run_crow0[run];
     const int AP = XP + 8;
+    // every thread checks one cluster for emptiness (needed only if the run continues)
+    int my_empty = 0;
+    if (threadIdx.x < K && acc_red[(long long)(crow0 + threadIdx.x) * AP + XP] <= 0) my_empty = 1;
+    const int any_empty = __syncthreads_or(my_empty);
     if (threadIdx.x == 0) {
         int go = 0;
         s_empty = 0;
@@ -395,14 +417,12 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             // (clustering/_clustering.py:129-132) and runs at most n_iter iterations (:118).
             if ((p >= 2 && changed == 0) || p >= n_iter) st[LEIDA_KM_ST_ACTIVE] = 0;
             else go = 1;
-            if (go) {
+            if (go && any_empty) {
                 for (int k = 0; k < K; ++k)
                     if (acc_red[(long long)(crow0 + k) * AP + XP] <= 0) { s_empty = k + 1; break; }
-                if (s_empty) {
-                    st[LEIDA_KM_ST_EMPTY] = s_empty;
-                    st[LEIDA_KM_ST_ACTIVE] = 0;
-                    go = 0;
-                }
+                st[LEIDA_KM_ST_EMPTY] = s_empty;
+                st[LEIDA_KM_ST_ACTIVE] = 0;
+                go = 0;
             }
             st[LEIDA_KM_ST_CHANGED] = 0;
             st[LEIDA_KM_ST_RECHECKED] = 0;
@@ -430,6 +450,24 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             if (lane == 0) cnorm[crow0 + k] = n;
         }
         __syncthreads();
+    }
+    // n_active[0] counts the runs that continue, n_active[1] the CTAs that have decided: the last
+    // one publishes {active runs, passes completed} to the host-visible mailbox and re-arms both.
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(&n_active[1], 1);
+        if (ticket == n_runs - 1) {
+            const int na = atomicAdd(&n_active[0], 0);
+            n_active[2] = na;                       // device copy of the last count
+            n_active[0] = 0;
+            n_active[1] = 0;
+            if (mailbox) {
+                mailbox[0] = na;
+                __threadfence_system();
+                mailbox[1] = mailbox[1] + 1;
+                __threadfence_system();
+            }
+        }
     }
     // tensor-core operands of this run at its packed position: unit-normalised centroids, bf16 hi/lo.
     // Written for every packed run (also one that just stopped), so the packed matrix never holds
@@ -705,7 +743,7 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
 extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
                                    const int64_t* acc_reduced, const int64_t* state_reduced, float* cent, double* cnorm,
                                    int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol, void* C1,
-                                   void* C2, leida_stream_t stream) {
+                                   void* C2, int32_t* mailbox, leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LEIDA_REQUIRE(run_k && run_crow0 && acc_reduced && state_reduced && cent && cnorm && state && n_active_out, "null pointer");
     int rc = check_runs(n_runs, N, x_pitch);
@@ -716,7 +754,7 @@ extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32
     const int NPK = (int)(((int64_t)N + 63) / 64 * 64);
     k_update<<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, (const long long*)acc_reduced,
                                      (const long long*)state_reduced, cent, cnorm, (long long*)state, n_iter, n_active_out,
-                                     run_pcol, (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK);
+                                     run_pcol, (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK, mailbox);
     return check_launch("k_update");
 }
 

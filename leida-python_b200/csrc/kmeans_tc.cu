@@ -114,17 +114,12 @@ __host__ __device__ __forceinline__ int read_width(int K) {
          : K <= 48 ? 48 : 64;
 }
 
-// Top-2 of a run's K scores read directly from TMEM.  The cluster index is packed into the 6 low
-// mantissa bits of each score (a 2^-17 relative perturbation, covered by the error bound), which
-// makes every key unique: best = max tree, second = max tree over the keys != best.  All trees are
-// fully unrolled over the read width, so the work is instruction-level parallel, not a chain.
-template <int W1, int W2>
-__device__ __forceinline__ void run_top2(uint32_t taddr, int K, float& best, float& second, int& bk) {
-    constexpr int W = W1 + W2;
-    uint32_t r[W];
-    tmem_ld<W1>(taddr, r);
-    tmem_ld<W2>(taddr + W1, r + W1);
-    tmem_ld_wait();
+// Top-2 of a run's K scores held in registers (read from TMEM).  The cluster index is packed into
+// the 6 low mantissa bits of each score (a 2^-17 relative perturbation, covered by the error bound),
+// which makes every key unique: best = max tree, second = max tree over the keys != best.  All trees
+// are fully unrolled over the read width, so the work is instruction-level parallel, not a chain.
+template <int W>
+__device__ __forceinline__ void top2_regs(const uint32_t* r, int K, float& best, float& second, int& bk) {
     float key[W];
 #pragma unroll
     for (int k = 0; k < W; ++k)
@@ -148,19 +143,12 @@ __device__ __forceinline__ void run_top2(uint32_t taddr, int K, float& best, flo
     second = __uint_as_float(__float_as_uint(m[0]) & 0xFFFFFFC0u);
 }
 
-__device__ __forceinline__ void run_top2_any(uint32_t taddr, int K, float& best, float& second, int& bk) {
-    switch (read_width(K)) {
-        case 4: run_top2<4, 0>(taddr, K, best, second, bk); break;
-        case 8: run_top2<8, 0>(taddr, K, best, second, bk); break;
-        case 12: run_top2<8, 4>(taddr, K, best, second, bk); break;
-        case 16: run_top2<16, 0>(taddr, K, best, second, bk); break;
-        case 20: run_top2<16, 4>(taddr, K, best, second, bk); break;
-        case 24: run_top2<16, 8>(taddr, K, best, second, bk); break;
-        case 32: run_top2<32, 0>(taddr, K, best, second, bk); break;
-        case 40: run_top2<32, 8>(taddr, K, best, second, bk); break;
-        case 48: run_top2<32, 16>(taddr, K, best, second, bk); break;
-        default: run_top2<64, 0>(taddr, K, best, second, bk); break;
-    }
+// The registers written by tcgen05.ld become valid only after tcgen05.wait::ld; this empty asm makes
+// every later use of them depend on a point after the wait.
+template <int W>
+__device__ __forceinline__ void reg_fence(uint32_t* r) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) asm volatile("" : "+r"(r[k]));
 }
 
 // Rare path, kept out of line: queue the (run,row) pair for the fp64 re-check, or resolve it here
@@ -170,7 +158,8 @@ __device__ __noinline__ int defer_row(const TcParams& p, int run, long long row,
 
 // Packing plan written by k_plan (device), read by the assign kernel.
 //   plan[0] = number of column tiles, plan[1] = number of packed (active) runs
-//   tile_first[t], tile_count[t] : slice of the packed run list that lives in tile t
+//   tile_first[t] & 0xffff, tile_count[t] : slice of the packed run list that lives in tile t;
+//   tile_first[t] >> 16 = TMEM read width of the tile's widest run
 //   prun[i] = run id, pcol[i] = (first column of the run inside its tile) | (K << 8)
 struct TcParams {
     long long M;
@@ -214,6 +203,58 @@ __device__ __noinline__ int defer_row(const TcParams& p, int run, long long row,
     }
     atomicAdd(reinterpret_cast<unsigned long long*>(p.state + (long long)run * kStateWordsTc + LEIDA_KM_ST_RECHECKED), 1ull);
     return out;
+}
+
+// Epilogue of one column tile for one warp: its runs are i = half, half+2, ... of the tile's run
+// list (at most 32 per warp, so one coalesced metadata load + shuffles).  Software pipelined: the
+// TMEM columns of the next run are in flight while the current run's top-2 is computed.
+template <int W1, int W2>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int first, int cnt, int half, int lane,
+                                              bool valid, float thr, int32_t* lab, long long row) {
+    constexpr int W = W1 + W2;
+    const int n_mine = (cnt - half + 1) >> 1;
+    if (n_mine <= 0) return;
+    const int mi = half + 2 * lane;
+    const int mine = mi < cnt ? first + mi : first;
+    const int m_run = p.prun[mine], m_col = p.pcol[mine];
+    uint32_t ra[W], rb[W <= 24 ? W : 1];
+    auto issue = [&](int b, uint32_t* r) {
+        const int c0 = __shfl_sync(0xffffffffu, m_col, b) & 0xff;
+        tmem_ld<W1>(taddr + c0, r);
+        tmem_ld<W2>(taddr + c0 + W1, r + W1);
+    };
+    auto finish = [&](int b, uint32_t* r) {
+        reg_fence<W>(r);
+        const int run = __shfl_sync(0xffffffffu, m_run, b);
+        const int K = __shfl_sync(0xffffffffu, m_col, b) >> 8;
+        float best, second;
+        int bk;
+        top2_regs<W>(r, K, best, second, bk);
+        if (valid) {
+            int out = bk;
+            if (!((best - second) > thr)) out = defer_row(p, run, row, K);
+            lab[(long long)run * p.M] = out;
+        }
+    };
+    if constexpr (W <= 24) {
+        issue(0, ra);
+        for (int b = 0; b < n_mine; b += 2) {
+            tmem_ld_wait();
+            if (b + 1 < n_mine) issue(b + 1, rb);
+            finish(b, ra);
+            if (b + 1 < n_mine) {
+                tmem_ld_wait();
+                if (b + 2 < n_mine) issue(b + 2, ra);
+                finish(b + 1, rb);
+            }
+        }
+    } else {                                  // wide runs: one register set (few runs per tile anyway)
+        for (int b = 0; b < n_mine; ++b) {
+            issue(b, ra);
+            tmem_ld_wait();
+            finish(b, ra);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -306,28 +347,22 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
             const float thr = valid ? p.tau * (float)p.xnorm[row] : 0.f;
             int32_t* lab = p.labels_new + row;
             for (int ct = 0; ct < n_ct; ++ct) {
-                const int first = p.tile_first[ct], cnt = p.tile_count[ct];
+                const int tf = p.tile_first[ct], cnt = p.tile_count[ct];
+                const int first = tf & 0xffff, wt = tf >> 16;      // wt = read width of the tile's widest run
                 mbar_wait(&tfull[acc], aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-                for (int i0 = half; i0 < cnt; i0 += 64) {
-                    const int mi = i0 + 2 * lane;
-                    const int mine = mi < cnt ? first + mi : first;
-                    const int m_run = p.prun[mine], m_col = p.pcol[mine];
-                    const int nb = min(32, (cnt - i0 + 1) >> 1);
-                    for (int b = 0; b < nb; ++b) {
-                        const int run = __shfl_sync(0xffffffffu, m_run, b);
-                        const int ck = __shfl_sync(0xffffffffu, m_col, b);
-                        const int c0 = ck & 0xff, K = ck >> 8;
-                        float best, second;
-                        int bk;
-                        run_top2_any(taddr + c0, K, best, second, bk);
-                        if (valid) {
-                            int out = bk;
-                            if (!((best - second) > thr)) out = defer_row(p, run, row, K);
-                            lab[(long long)run * p.M] = out;
-                        }
-                    }
+                switch (wt) {
+                    case 4: epilogue_tile<4, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 8: epilogue_tile<8, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 12: epilogue_tile<8, 4>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 16: epilogue_tile<16, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 20: epilogue_tile<16, 4>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 24: epilogue_tile<16, 8>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 32: epilogue_tile<32, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 40: epilogue_tile<32, 8>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 48: epilogue_tile<32, 16>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    default: epilogue_tile<64, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);            // accumulator may be overwritten by the next tile
@@ -373,6 +408,7 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
        int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol, int32_t* run_pcol) {
     __shared__ short s_k[PLAN_MAX_RUNS];        // K, or 0 when the run is not active
     __shared__ int s_pc[PLAN_MAX_RUNS];         // packed global column or -1
+    __shared__ short s_tw[PLAN_MAX_RUNS];       // read width of the widest (= last placed) run of each tile
     __shared__ int s_tiles, s_np;
     for (int r = threadIdx.x; r < n_runs; r += blockDim.x)
         s_k[r] = state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] != 0 ? (short)run_k[r] : (short)0;
@@ -385,6 +421,7 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
             if (K > 0) {
                 if (col + read_width(K) > BN) { ++tile; col = 0; }   // the TMEM read of the run must stay inside the tile
                 pc = tile * BN + col;
+                s_tw[tile] = (short)read_width(K);     // runs arrive in ascending K: the last one is the widest
                 col += K;
                 ++np;
             }
@@ -421,7 +458,7 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
                 prun[idx] = r;
                 pcol[idx] = (s_pc[r] - t * BN) | ((int)s_k[r] << 8);
                 atomicAdd(&tile_count[t], 1);
-                if (s_pc[r] == t * BN) tile_first[t] = idx;       // the run that opens the tile
+                if (s_pc[r] == t * BN) tile_first[t] = idx | ((int)s_tw[t] << 16);   // the run that opens the tile
             }
         }
         base += s_scan[255];
@@ -460,7 +497,7 @@ __global__ void k_pack_centroids(const int32_t* __restrict__ run_k, const int32_
 // cluster in shared memory; then thread (g, j) sums column j over its share of the rows entering
 // (leaving) cluster k in a REGISTER -- independent loads, no read-modify-write chain -- and issues one
 // global int64 atomic per (cluster, column) it touched.  Integer sums: any grouping gives the same result.
-constexpr int APPLY_ROWS = 1024;
+constexpr int APPLY_ROWS = 4096;
 constexpr int APPLY_THREADS = 256;
 
 __device__ __forceinline__ long long quant40(float v) { return __double2ll_rn((double)v * 1099511627776.0); }
@@ -470,17 +507,19 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
              const int32_t* __restrict__ prun, const int32_t* __restrict__ run_k,
              const int32_t* __restrict__ run_crow0, int32_t* __restrict__ labels_cur,
              const int32_t* __restrict__ labels_new, long long* acc, long long* state) {
-    if ((int)blockIdx.y >= plan[1]) return;
-    const int run = prun[blockIdx.y];
-    if (state[(long long)run * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) return;
     __shared__ int s_list[APPLY_ROWS];       // local row | old<<16 | new<<24
     __shared__ short s_in[APPLY_ROWS];       // local rows sorted by NEW cluster
     __shared__ short s_out[APPLY_ROWS];      // local rows sorted by OLD cluster (old >= 0 only)
     __shared__ int s_cin[LEIDA_KM_MAX_K + 1], s_cout[LEIDA_KM_MAX_K + 1], s_pin[LEIDA_KM_MAX_K], s_pout[LEIDA_KM_MAX_K];
     __shared__ int s_n;
-    const int K = run_k[run], crow0 = run_crow0[run];
     const int AP = XP + 8;
     const long long row_base = (long long)blockIdx.x * APPLY_ROWS;
+    const int n_packed = plan[1];
+  for (int pr = blockIdx.y; pr < n_packed; pr += gridDim.y) {      // persistent over the packed runs
+    const int run = prun[pr];
+    if (state[(long long)run * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) continue;
+    const int K = run_k[run], crow0 = run_crow0[run];
+    __syncthreads();
     int32_t* cur = labels_cur + (long long)run * M;
     const int32_t* nw = labels_new + (long long)run * M;
     if (threadIdx.x == 0) s_n = 0;
@@ -492,7 +531,7 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
             const int o = cur[row], n = nw[row];
             if (o != n) {
                 cur[row] = n;
-                s_list[atomicAdd(&s_n, 1)] = r | ((o & 0xff) << 16) | (n << 24);
+                s_list[atomicAdd(&s_n, 1)] = r | ((o & 0xff) << 16) | (n << 24);   // r < 4096 < 2^16
                 atomicAdd(&s_cin[n], 1);
                 if (o >= 0) atomicAdd(&s_cout[o], 1);
             }
@@ -500,7 +539,7 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     }
     __syncthreads();
     const int nchg = s_n;
-    if (nchg == 0) return;
+    if (nchg == 0) continue;
     if (threadIdx.x == 0) {          // exclusive prefix sums (K <= 64)
         int a = 0, b = 0;
         for (int k = 0; k < K; ++k) {
@@ -546,6 +585,7 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     if (threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(state + (long long)run * kStateWordsTc + LEIDA_KM_ST_CHANGED),
                   (unsigned long long)nchg);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -633,16 +673,26 @@ extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const floa
     TcParams p;
     p.M = M; p.nkb = NPK / BK; p.plan = plan; p.tile_first = tile_first; p.tile_count = tile_count;
     p.prun = prun; p.pcol = pcol; p.run_k = run_k; p.xnorm = xnorm;
-    // Error bound of a score (|x| units): dropped split terms 3*2^-18, normalisation of c 2^-22, fp32
-    // accumulation of 3*NPK products in the tensor core (<= 2^-22 each, not assumed round-to-nearest);
-    // index packing in the epilogue truncates 6 mantissa bits (2^-17); doubled for the difference of
-    // two scores, 25% slack.
-    p.tau = 2.5f * (3.0f * 3.8147e-6f + 2.4e-7f + 7.63e-6f + 3.0f * (float)NPK * 2.3842e-7f);
+    // Error bound of a score, in units of |x| (the centroids are unit vectors, so sum|x_j c_j| <= |x|):
+    //   dropped split terms x2*c2, x*rc, rx*c                       3 * 2^-18
+    //   fp32 normalisation of the centroid                           2^-22
+    //   index packing in the epilogue (6 mantissa bits)              2^-17
+    //   fp32 accumulation in the tensor core: 3*NPK/16 MMAs per output, each a 16-term sum plus the add
+    //   into the accumulator -- (1 + log2 16) = 5 roundings of at most one fp32 ulp (2^-23, truncation
+    //   allowed) of a partial sum that never exceeds |x|; counted twice for safety.
+    // The margin compares two scores (x2), plus 25% slack.  tests/test_gpu_parity.py checks the bound
+    // against fp64 (labels of the tensor-core path == labels of the fp32 CUDA-core path == oracle).
+    const float acc_term = 2.0f * (3.0f * (float)(NPK / 16) * 5.0f) * 1.1921e-7f;
+    p.tau = 2.5f * (3.0f * 3.8147e-6f + 2.4e-7f + 7.63e-6f + acc_term);
     p.labels_new = labels_new; p.worklist = worklist; p.worklist_cap = worklist_cap;
     p.X = X; p.XP = (int)x_pitch; p.N = N; p.cent = cent; p.cnorm = cnorm; p.run_crow0 = run_crow0;
     p.state = (long long*)state;
     const size_t smem = 1024 + (size_t)ST * STAGE_BYTES + 32 * sizeof(uint64_t);
-    LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_tc_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;      // once per process; keeps the call legal inside stream capture
+    if (!attr_set) {
+        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_tc_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     const int n_rt = (int)((M + BM - 1) / BM);
     const int grid = n_rt < sm_count() ? n_rt : sm_count();
     k_tc_assign<<<grid, TC_THREADS, smem, st>>>(mx1, mx2, mc1, mc2, p);
@@ -655,7 +705,7 @@ extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x
                                      int64_t* acc, int64_t* state, leida_stream_t stream) {
     LEIDA_REQUIRE(X && plan && prun && run_k && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
     LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && n_runs_bound >= 1 && n_runs_bound <= 65535, "sizes");
-    dim3 grid((unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS), (unsigned)n_runs_bound);
+    dim3 grid((unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS), (unsigned)(n_runs_bound < 48 ? n_runs_bound : 48));
     k_diff_apply<<<grid, APPLY_THREADS, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, plan, prun, run_k, run_crow0,
                                                                    labels_cur, labels_new, (long long*)acc,
                                                                    (long long*)state);

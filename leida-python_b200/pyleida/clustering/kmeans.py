@@ -18,6 +18,7 @@ _KP_BUCKETS = (4, 8, 12, 16, 20, 24, 32, 40, 48, 64)
 # 'tc': tcgen05 tensor-core assignment (production path); 'simt': fp32 CUDA-core kernel kept for
 # cross-checking the two implementations against each other in the tests.
 DEFAULT_ASSIGN = os.environ.get("LEIDA_KMEANS_ASSIGN", "tc")
+USE_CUDA_GRAPHS = os.environ.get("LEIDA_CUDA_GRAPHS", "1") != "0"
 
 
 def _bucket(k):
@@ -71,10 +72,29 @@ class KMeansEngine:
             self._x12 = (x1, x2, npk)
         return self._x12
 
+    def _capture(self, do_assign, do_rest, split):
+        """CUDA graphs of one lock-step pass: [assign + rest], or [assign], [rest] when the assign
+        kernel has to be timed on its own."""
+        torch = self.torch
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graphs = []
+        with torch.cuda.stream(side):
+            for parts in ((do_assign,), (do_rest,)) if split else ((do_assign, do_rest),):
+                g = torch.cuda.CUDAGraph()
+                g.capture_begin()
+                for fn in parts:
+                    fn()
+                g.capture_end()
+                graphs.append(g)
+        torch.cuda.current_stream().wait_stream(side)
+        return graphs
+
     def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1, profile=None, assign=None):
         """runs: list of (k, init_rows) with init_rows = k global row indices.  Returns BatchResult.
-        profile: optional list; (start, stop) CUDA event pairs bracketing every assign-kernel launch
-        are appended to it (bench.py's live roofline measurement)."""
+        profile: optional dict; for every kernel name present as a key ("assign", "recheck", "apply",
+        "update", "plan"; or all of them with {"*": True}) the (start, stop) CUDA event pairs bracketing
+        each launch are appended to profile[name] (bench.py's live roofline measurement)."""
         torch = self.torch
         if centroid_update not in ("exact", "reference"):
             raise ValueError("centroid_update must be 'exact' or 'reference'")
@@ -111,7 +131,9 @@ class KMeansEngine:
         cap = int(min(max(R * self.M // 8, 1 << 16), 1 << 24))    # (run,row) pairs queued for the fp64 re-check per pass
         worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
         worklist[:8].zero_()
-        n_active = torch.zeros(1, dtype=torch.int32, device=dev)
+        n_active = torch.zeros(4, dtype=torch.int32, device=dev)
+        mailbox = torch.zeros(2, dtype=torch.int32, pin_memory=True)   # written by the last CTA of leida_kmeans_update
+        mb = mailbox.numpy()
         st = nv.stream()
 
         if self.comm.world > 1:
@@ -128,17 +150,16 @@ class KMeansEngine:
             acc_red, state_red = acc, state
 
         def timed(name, fn):
-            want = profile is not None and (name in profile if isinstance(profile, dict) and profile else
-                                            name == "assign" or isinstance(profile, dict))
-            if not want:
+            if profile is None or not (profile.get("*") or name in profile):
                 return fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
             e1.record()
-            (profile.setdefault(name, []) if isinstance(profile, dict) else profile).append((e0, e1))
+            profile.setdefault(name, []).append((e0, e1))
 
-        if assign == "tc":
+        tc = assign == "tc"
+        if tc:
             x1, x2, npk = self._tc_operands()
             c_rows = (2 * CR + 128 + 127) // 128 * 128
             c1 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
@@ -151,105 +172,106 @@ class KMeansEngine:
             pcol = torch.zeros(R, dtype=torch.int32, device=dev)
             run_pcol = torch.zeros(R, dtype=torch.int32, device=dev)
 
-            def tc_plan(pack):
-                timed("plan", lambda: nv.call(
-                    "leida_kmeans_tc_plan", R, nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm),
+        def tc_plan():
+            nv.call("leida_kmeans_tc_plan", R, nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm),
                     self.N, self.XP, nv.ptr(plan), nv.ptr(tile_first), nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol),
-                    nv.ptr(run_pcol), nv.ptr(c1), nv.ptr(c2), int(pack), st))
+                    nv.ptr(run_pcol), nv.ptr(c1), nv.ptr(c2), 1, nv.stream())
 
-            def tc_pass():
-                timed("assign", lambda: nv.call(
-                    "leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
-                    self.N, nv.ptr(c1), nv.ptr(c2), c_rows, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(plan), nv.ptr(tile_first),
-                    nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels_new),
-                    nv.ptr(state), nv.ptr(worklist), cap, st))
-                timed("recheck", lambda: nv.call(
-                    "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, nv.ptr(run_k),
-                    nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
-                    nv.ptr(worklist), cap, nv.ptr(labels_new), st))
-                timed("apply", lambda: nv.call(
-                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(packed_bound[0]), nv.ptr(plan),
-                    nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
-                    nv.ptr(state), st))
-
-            packed_bound = [R]          # host-side upper bound of the number of packed runs (plan[1] on the device)
-            tc_plan(True)
-        # groups of consecutive (K-sorted) runs sharing a register tile
+        # groups of consecutive (K-sorted) runs sharing a register tile (SIMT flow only)
         groups, g0 = [], 0
         for i in range(1, R + 1):
             if i == R or _bucket(int(ks[i])) != _bucket(int(ks[g0])):
                 groups.append((g0, i, int(ks[g0:i].max())))
                 g0 = i
-        # Lock-step passes.  The host never blocks on the GPU inside the loop: after every pass the
-        # active-run count is copied to a pinned ring slot and the host reads slots whose copy has
-        # completed, so it runs a few passes ahead (passes issued after every run has stopped are
-        # no-ops: stopped runs are skipped by every kernel).  The count is non-increasing, so a stale
-        # value is a valid upper bound: it sizes the apply grid and triggers re-packing of the
-        # tensor-core operands once enough runs have stopped.
-        ring = 8
-        flags = torch.empty(ring, dtype=torch.int32, pin_memory=True)
-        flags.fill_(R)
-        flags_np = flags.numpy()
-        events = [None] * ring
-        passes = 0
-        launches = 0
-        active_bound = R
-        done = False
-        while not done:
-            if assign == "tc":
-                tc_pass()
-                launches += 3
-            for (a, b, kmax) in (groups if assign == "simt" else ()):
-                timed("assign", lambda: nv.call(
-                    "leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
-                    run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
-                    labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
-                    nv.ptr(worklist), cap, st))
+
+        def do_assign():
+            stq = nv.stream()
+            if tc:
+                nv.call("leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
+                        self.N, nv.ptr(c1), nv.ptr(c2), c_rows, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(plan), nv.ptr(tile_first),
+                        nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels_new),
+                        nv.ptr(state), nv.ptr(worklist), cap, stq)
+                return
+            for (a, b, kmax) in groups:
+                nv.call("leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
+                        run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
+                        labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
+                        nv.ptr(worklist), cap, stq)
                 nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
-                        nv.ptr(worklist), cap, None, st)
-                launches += 2
+                        nv.ptr(worklist), cap, None, stq)
+
+        def do_rest():
+            stq = nv.stream()
+            if tc:
+                timed("recheck", lambda: nv.call(
+                    "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, nv.ptr(run_k),
+                    nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
+                    nv.ptr(worklist), cap, nv.ptr(labels_new), stq))
+                timed("apply", lambda: nv.call(
+                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(plan),
+                    nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
+                    nv.ptr(state), stq))
             if self.comm.world > 1:
                 acc_red.copy_(acc)
                 state_red.copy_(state)
                 self.comm.all_reduce_sum_(acc_red)
                 self.comm.all_reduce_sum_(state_red)
-            if assign == "tc" and 0 < active_bound <= 0.8 * packed_bound[0]:
-                tc_plan(False)                       # uses the activity flags of the previous update
-                packed_bound[0] = active_bound
-                launches += 1
             timed("update", lambda: nv.call(
                 "leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
                 nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
-                nv.ptr(run_pcol) if assign == "tc" else None, nv.ptr(c1) if assign == "tc" else None,
-                nv.ptr(c2) if assign == "tc" else None, st))
-            launches += 1
+                nv.ptr(run_pcol) if tc else None, nv.ptr(c1) if tc else None, nv.ptr(c2) if tc else None,
+                mailbox.data_ptr(), stq))
             if centroid_update == "reference":
                 nv.call("leida_kmeans_means_f32_sequential", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_k),
-                        nv.ptr(run_c0), nv.ptr(labels), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm), st)
-                launches += 2
-                if assign == "tc":
-                    tc_plan(True)                    # the float32 sequential means replace the centroids: re-pack
-                    launches += 2
-            slot = passes % ring
-            if events[slot] is not None:
-                events[slot].synchronize()            # ring full: wait for the oldest copy only ...
-                active_bound = min(active_bound, int(flags_np[slot]))   # ... and use its value before the slot is reused
-            flags[slot:slot + 1].copy_(n_active, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            events[slot] = ev
-            passes += 1
-            for i in range(ring):                     # newest completed count
-                j = (slot - i) % ring
-                if events[j] is not None and events[j].query():
-                    active_bound = min(active_bound, int(flags_np[j]))
+                        nv.ptr(run_c0), nv.ptr(labels), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm), stq)
+                if tc:
+                    tc_plan()                          # the float32 sequential means replace the centroids: re-pack
+
+        launches_per_pass = (3 if tc else 2 * len(groups)) + 1 + (2 if centroid_update == "reference" else 0)
+        if tc:
+            tc_plan()
+        # Lock-step passes.  The first pass runs eagerly; the following ones replay CUDA graphs of the
+        # (static) launch sequence.  The host never synchronises inside the loop: the last CTA of
+        # leida_kmeans_update stores {runs still active, passes completed} in a pinned mailbox, which
+        # the host reads to stop, to bound its run-ahead, and to re-pack the tensor-core operands once
+        # enough runs have stopped (the active count never increases, so a stale value is a valid
+        # upper bound; passes issued after every run has stopped are no-ops).
+        use_graph = tc and centroid_update == "exact" and USE_CUDA_GRAPHS
+        time_assign = profile is not None and (profile.get("*") or "assign" in profile)
+        eager_rest = profile is not None and any(k in profile for k in ("*", "recheck", "apply", "update"))
+        max_lag = 6
+        mb[:] = 0
+        packed_bound = R
+        active_bound = R
+        issued = 0
+        graphs = None
+        while True:
+            if tc and 0 < active_bound <= 0.8 * packed_bound:
+                tc_plan()                              # re-pack: only the runs still active keep tensor-core columns
+                packed_bound = active_bound
+            if use_graph and issued == 1 and not eager_rest:
+                graphs = self._capture(do_assign, do_rest, split=time_assign)
+            if graphs is None:
+                timed("assign", do_assign)
+                do_rest()
+            elif len(graphs) == 2:
+                timed("assign", graphs[0].replay)
+                graphs[1].replay()
+            else:
+                graphs[0].replay()
+            issued += 1
+            while issued - int(mb[1]) > max_lag:
+                pass
+            if mb[1] >= 1:
+                active_bound = min(active_bound, int(mb[0]))
+                if active_bound == 0:
                     break
-            if active_bound == 0:
-                done = True
-            if passes > n_iter + 2 + ring:
+            if issued > n_iter + 2 + max_lag:
                 raise nv.LeidaCudaError("k-means did not terminate (internal error)")
+        passes = issued
+        launches = issued * launches_per_pass
         nv.call("leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
                 nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), st)
         launches += 2

@@ -25,7 +25,7 @@ for rep in range(3):
     t2 = sync()
     runs, plan = sweep_runs(M, 2, 20, 15, None, inits)
     t3 = sync()
-    prof = {}
+    prof = {"*": True}
     l0 = nv.launch_count()
     res = eng.run(runs, profile=prof if rep == 2 else None)
     t4 = sync()
@@ -36,6 +36,7 @@ for rep in range(3):
     print(f"  assign={res.assign} rechecked {res.rechecked_total} of {res.total_passes() * M} row-passes "
           f"({res.rechecked_total / (res.total_passes() * M):.2e}), label changes {res.changed_total}")
     for name, evs in prof.items():
+        if name == "*": continue
         t = [a.elapsed_time(b) for a, b in evs]
         print(f"  {name:8s} total {sum(t):8.2f} ms  n={len(t)}  first {t[0]:.3f}  median {np.median(t):.3f}  max {max(t):.3f}")
 # active runs per pass histogram
