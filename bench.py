@@ -276,12 +276,14 @@ def native_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     last = None
+    graph_launches = 0
     for _ in range(args.steps):
         last = step_device(profile)
+        graph_launches += last.batch.graph_launches
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    launches = nvl.launch_count() - l0
+    launches = nvl.launch_count() - l0 + graph_launches     # kernels inside replayed CUDA graphs are counted by the engine
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     ln = torch.tensor([launches], dtype=torch.int64, device=dev)

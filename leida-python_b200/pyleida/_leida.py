@@ -17,6 +17,17 @@ from .parallel import Comm
 from .pipeline import run_device
 
 
+_POOL = None
+
+
+def _staging_pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4)
+    return _POOL
+
+
 class Bunch(dict):
     """dict with attribute access (the reference returns sklearn.utils.Bunch objects, _leida.py:377-389)."""
     __getattr__ = dict.__getitem__
@@ -132,9 +143,20 @@ class Leida:
                 j += 1
             host = torch.empty((j - i, N, T), dtype=torch.float64, pin_memory=True)
             hv = host.numpy()
-            for b, s in enumerate(ids[i:j]):
-                hv[b] = self.time_series[s]
-            blocks.append(host.to(dev, non_blocking=True))
+            dev_block = torch.empty((j - i, N, T), dtype=torch.float64, device=dev)
+            # stage in slices: worker threads fill pinned memory (numpy copies release the GIL) while
+            # the previous slice is already on its way over PCIe
+            step = max(1, (j - i + 7) // 8)
+
+            def fill(lo, hi, base=i):
+                for b in range(lo, hi):
+                    hv[b] = self.time_series[ids[base + b]]
+            for lo in range(0, j - i, step):
+                hi = min(j - i, lo + step)
+                parts = np.array_split(np.arange(lo, hi), min(4, hi - lo))
+                list(_staging_pool().map(lambda p: fill(int(p[0]), int(p[-1]) + 1), [p for p in parts if len(p)]))
+                dev_block[lo:hi].copy_(host[lo:hi], non_blocking=True)
+            blocks.append(dev_block)
             self.h2d_bytes += host.numel() * 8
             i = j
         # per-volume metadata (_leida.py:290-297) and the metric groups
@@ -160,15 +182,27 @@ class Leida:
         self.kmeans_batch_ = res.batch
         # device -> host: labels, centroids, integer metric tables, eigenvectors
         ks = list(range(self._K_min_, self._K_max_ + 1))
-        labels = res.labels.cpu().numpy()
-        occ, runs, trans = res.occ.cpu().numpy(), res.runs.cpu().numpy(), res.trans.cpu().numpy()
+        def to_host(t):
+            """device -> pinned host, asynchronous; synchronised once below"""
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+        pinned = {"labels": to_host(res.labels), "occ": to_host(res.occ), "runs": to_host(res.runs),
+                  "trans": to_host(res.trans)}
+        for k in ks:
+            pinned[f"c{k}"] = to_host(res.models[k].centers_device_)
+        if keep_eigenvectors:
+            pinned["lei"] = to_host(res.lei64)
+        torch.cuda.current_stream().synchronize()
+        labels = pinned["labels"].numpy()
+        occ, runs, trans = pinned["occ"].numpy(), pinned["runs"].numpy(), pinned["trans"].numpy()
         self.d2h_bytes += labels.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
         predictions = pd.DataFrame({"subject_id": sub_list, "condition": cond_list})
         models, perf = {}, []
         for c, k in enumerate(ks):
             km = res.models[k]
             km.labels_ = labels[c].astype(np.int64)
-            km.cluster_centers_ = km.centers_device_.cpu().numpy()
+            km.cluster_centers_ = pinned[f"c{k}"].numpy().copy()
             self.d2h_bytes += km.cluster_centers_.nbytes
             models[f"k_{k}"] = km
             predictions[f"k_{k}"] = km.labels_
@@ -176,7 +210,7 @@ class Leida:
                          "Davies-Bouldin_score": np.nan})
         self._lei_host = None
         if keep_eigenvectors:
-            self._lei_host = res.lei64.cpu().numpy()
+            self._lei_host = pinned["lei"].numpy()         # stays in the pinned buffer (no second copy)
             self.d2h_bytes += self._lei_host.nbytes
         from .dynamics_metrics.metrics import tables_from_counts
         dynamics = tables_from_counts([f"k_{k}" for k in ks], res.col_k, segments, occ, runs, trans, TR)

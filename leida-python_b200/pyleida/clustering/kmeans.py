@@ -248,7 +248,7 @@ class KMeansEngine:
         issued = 0
         graphs = None
         while True:
-            if tc and 0 < active_bound <= 0.8 * packed_bound:
+            if tc and 0 < active_bound <= 0.9 * packed_bound:
                 tc_plan()                              # re-pack: only the runs still active keep tensor-core columns
                 packed_bound = active_bound
             if use_graph and issued == 1 and not eager_rest:
@@ -272,6 +272,7 @@ class KMeansEngine:
                 raise nv.LeidaCudaError("k-means did not terminate (internal error)")
         passes = issued
         launches = issued * launches_per_pass
+        graph_launches = (issued - 1) * launches_per_pass if graphs is not None else 0   # not seen by the C-side counter
         nv.call("leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
                 nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), st)
         launches += 2
@@ -298,6 +299,7 @@ class KMeansEngine:
         out.rechecked_total = int(st_host[:, nv.ST_RECHECK_TOTAL].sum())
         out.changed_total = int(st_host[:, nv.ST_CHANGED_TOTAL].sum())
         out.assign = assign
+        out.graph_launches = graph_launches
         return out
 
     def predict(self, centers):

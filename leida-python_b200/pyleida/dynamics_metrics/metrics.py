@@ -24,6 +24,16 @@ class Segments:
     def __len__(self):
         return len(self.subjects)
 
+    def subjects_array(self):
+        if getattr(self, "_sa", None) is None:
+            self._sa = np.asarray(self.subjects, dtype=object)
+        return self._sa
+
+    def conditions_array(self):
+        if getattr(self, "_ca", None) is None:
+            self._ca = np.asarray(self.conditions, dtype=object)
+        return self._ca
+
     @classmethod
     def from_metadata(cls, metadata):
         sub = np.asarray(metadata["subject_id"].values if hasattr(metadata, "columns") else metadata[0])
@@ -164,21 +174,22 @@ def _group_tables(metadata, labels, segments=None):
     return seg, k, occ[0], runs[0], trans[0]
 
 
-def _state_frame(seg, values, k):
+def _frame(seg, values, cols):
+    """DataFrame(subject_id, condition, *cols) built in one go (column inserts are slow)."""
     import pandas as pd
-    df = pd.DataFrame(values, columns=[f"PL_state_{i + 1}" for i in range(k)])
-    df.insert(0, "subject_id", seg.subjects)
-    df.insert(1, "condition", seg.conditions)
-    return df
+    data = {"subject_id": seg.subjects_array(), "condition": seg.conditions_array()}
+    values = np.ascontiguousarray(values)
+    for i, c in enumerate(cols):
+        data[c] = values[:, i]
+    return pd.DataFrame(data, copy=False)
+
+
+def _state_frame(seg, values, k):
+    return _frame(seg, values, [f"PL_state_{i + 1}" for i in range(k)])
 
 
 def _transition_frame(seg, values, k):
-    import pandas as pd
-    cols = [f"From_{i + 1}_to_{j + 1}" for i in range(k) for j in range(k)]
-    df = pd.DataFrame(values.reshape(len(seg), k * k), columns=cols)
-    df.insert(0, "subject_id", seg.subjects)
-    df.insert(1, "condition", seg.conditions)
-    return df
+    return _frame(seg, values.reshape(len(seg), k * k), [f"From_{i + 1}_to_{j + 1}" for i in range(k) for j in range(k)])
 
 
 def _no_io(save_results):

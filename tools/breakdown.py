@@ -44,3 +44,10 @@ p = np.sort(res._passes)
 print("passes per run: min/median/mean/max", p.min(), np.median(p), p.mean(), p.max())
 for q in (10, 20, 30, 40, 60, 80, 100, 150):
     print(f"  runs still active after {q} passes: {(p > q).sum()}")
+
+# per-pass series (ms) for the first passes, from the last profiled run
+for name, evs in prof.items():
+    if name == "*": continue
+    t = [a.elapsed_time(b) for a, b in evs]
+    print(name, "passes 0-47:", " ".join(f"{v:.2f}" for v in t[:48]))
+    print(name, "sum 0-9 %.2f | 10-39 %.2f | 40-99 %.2f | 100+ %.2f" % (sum(t[:10]), sum(t[10:40]), sum(t[40:100]), sum(t[100:])))
