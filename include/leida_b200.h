@@ -218,8 +218,10 @@ int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_cro
                         int32_t* mailbox, leida_stream_t stream);
 /* n_active_out: device int32[4], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
  * [2] = runs still active after this call).  mailbox (may be NULL): HOST-visible (pinned, mapped)
- * int32[2]; the last CTA stores {runs still active, number of update calls completed} there so the
- * host can follow convergence without synchronising or copying. */
+ * int32[4]; the last CTA stores {runs still active, number of update calls completed, index of the
+ * first update call that left no run active (0 = not yet)} there so the host can follow convergence
+ * without synchronising or copying.  With several ranks the values are identical on every rank (they
+ * derive from all-reduced counters), which lets all ranks issue the same number of passes. */
 /* run_pcol / C1 / C2 (all NULL in the SIMT flow): the tensor-core operands of every packed run --
  * unit-normalised centroids split into bf16 hi/lo rows at the run's packed column -- are rewritten
  * here, so the next leida_kmeans_tc_assign needs no separate packing launch. */

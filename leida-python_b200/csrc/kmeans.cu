@@ -462,9 +462,11 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             n_active[0] = 0;
             n_active[1] = 0;
             if (mailbox) {
+                const int done = mailbox[1] + 1;
                 mailbox[0] = na;
+                if (na == 0 && mailbox[2] == 0) mailbox[2] = done;   // first update call after which no run is active
                 __threadfence_system();
-                mailbox[1] = mailbox[1] + 1;
+                mailbox[1] = done;
                 __threadfence_system();
             }
         }

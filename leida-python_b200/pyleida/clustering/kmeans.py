@@ -132,7 +132,7 @@ class KMeansEngine:
         worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
         worklist[:8].zero_()
         n_active = torch.zeros(4, dtype=torch.int32, device=dev)
-        mailbox = torch.zeros(2, dtype=torch.int32, pin_memory=True)   # written by the last CTA of leida_kmeans_update
+        mailbox = torch.zeros(4, dtype=torch.int32, pin_memory=True)   # written by the last CTA of leida_kmeans_update
         mb = mailbox.numpy()
         st = nv.stream()
 
@@ -248,7 +248,7 @@ class KMeansEngine:
         issued = 0
         graphs = None
         while True:
-            if tc and 0 < active_bound <= 0.9 * packed_bound:
+            if tc and mb[2] == 0 and 0 < active_bound <= 0.9 * packed_bound:
                 tc_plan()                              # re-pack: only the runs still active keep tensor-core columns
                 packed_bound = active_bound
             if use_graph and issued == 1 and not eager_rest:
@@ -266,9 +266,13 @@ class KMeansEngine:
                 pass
             if mb[1] >= 1:
                 active_bound = min(active_bound, int(mb[0]))
-                if active_bound == 0:
-                    break
-            if issued > n_iter + 2 + max_lag:
+            # Stop rule, identical on every rank (the collectives inside the passes must match): the
+            # device records the pass p0 after which no run was active; because the host checks after
+            # every issue and is never more than max_lag passes ahead, issued <= p0 + max_lag when p0
+            # becomes visible, and every rank issues exactly p0 + max_lag passes.
+            if mb[2] > 0 and issued >= int(mb[2]) + max_lag:
+                break
+            if issued > n_iter + 2 + 2 * max_lag:
                 raise nv.LeidaCudaError("k-means did not terminate (internal error)")
         passes = issued
         launches = issued * launches_per_pass
