@@ -312,3 +312,109 @@ def test_pipeline_ragged_and_per_volume_conditions(P, O):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+# ---- wider coverage -----------------------------------------------------------------------
+def test_config1_full_sweep_vs_oracle(P, O):
+    """BASELINE config 1 (20 x 90 x 200), the whole pipeline, K=2..20, random_state=0 (the reference's
+    semantics: identical restarts), against the CPU oracle."""
+    from pyleida import synthetic
+    ts, classes = synthetic.make_dataset(20, 90, 200, "states")
+    m = P.Leida.from_arrays(ts, classes).fit_predict(TR=0.72, random_state=0)
+    ref = O.execute_all(ts, classes, TR=0.72, K_min=2, K_max=20, n_init=1, random_state=0)
+    assert eig_ok(m.eigenvectors.iloc[:, 2:].values, ref["eigenvectors"])
+    for k in range(2, 21):
+        assert np.array_equal(m.predictions[f"k_{k}"].values, ref["models"][k].labels_), k
+        assert m.load_model(k).inertia_ == pytest.approx(ref["models"][k].inertia_, rel=1e-6)
+        for name in ("occupancies", "dwell_times", "transitions"):
+            assert np.array_equal(getattr(m._dynamics_, name)[f"k_{k}"].iloc[:, 2:].values, ref["metrics"][k][name]), (k, name)
+
+
+def test_tensor_core_and_cuda_core_assignment_agree(P):
+    """The tcgen05 path and the fp32 CUDA-core path must give identical labels, pass counts and
+    inertia (both are the fp64 argmin by construction) -- on iid data, the worst case for margins,
+    and on wide rows (N=1000 -> 16 k-blocks)."""
+    rng = np.random.default_rng(3)
+    for M, N, ks in ((30_000, 116, (2, 7, 20)), (5_000, 1000, (3, 20)), (9_000, 64, (40,))):
+        X = rng.standard_normal((M, N)).astype(np.float32)
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        eng = P.clustering.KMeansEngine(X)
+        runs = [(k, rng.choice(M, k, replace=False)) for k in ks for _ in range(2)]
+        a = eng.run(runs, n_iter=25, assign="tc")
+        b = eng.run(runs, n_iter=25, assign="simt")
+        for i in range(len(runs)):
+            assert a.passes(i) == b.passes(i), (M, N, i)
+            assert a.inertia(i) == b.inertia(i), (M, N, i)
+            assert bool((a.labels_device(i) == b.labels_device(i)).all()), (M, N, i)
+        assert a.rechecked_total < 0.05 * a.total_passes() * M      # the fp64 re-check stays a rare path
+
+
+def test_wide_rows_rank2_and_dense_eigenvectors(P, O):
+    """N = 1000 ROIs (BASELINE config 4 shape, few volumes): closed form and general solver."""
+    from pyleida import synthetic
+    x = synthetic.subject_series(5, 1000, 30, "states")
+    ph = O.hilbert_phase(x)
+    ref = O.leading_eigvec_rank2(ph)
+    assert eig_ok(P.signal_tools.eigenvectors_from_phases(ph), ref)
+    lei, _ = P.signal_tools.leading_eigenvectors(x[None])
+    assert eig_ok(lei, ref)
+    got, info = P.signal_tools.get_eigenvectors(P.signal_tools.phase_coherence(ph), return_info=True)
+    assert info["unconverged"] == 0 and info["iterations"] <= 4
+    assert eig_ok(got, ref)
+
+
+def test_empty_cluster_policy(P):
+    """Two identical initial rows: the second centroid never wins a tie (first minimum), so its
+    cluster is empty after the first pass.  The reference would carry NaN centroids; here the run is
+    flagged and discarded."""
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((500, 12)).astype(np.float32)
+    X[7] = X[3]
+    bad, good = np.array([3, 7, 11]), np.array([1, 2, 5])
+    km = P.clustering.KMeansLeida(k=3, n_init=2)
+    with pytest.warns(UserWarning):
+        km.fit(X, init_indices=[bad, good])
+    assert km.best_init_ == 1 and np.isnan(km.inertia_runs_[0]) and np.isfinite(km.inertia_)
+    with pytest.raises(RuntimeError):
+        P.clustering.KMeansLeida(k=3, n_init=1).fit(X, init_indices=[bad])
+
+
+def test_kmeans_argument_errors(P):
+    X = np.random.default_rng(0).standard_normal((50, 8)).astype(np.float32)
+    eng = P.clustering.KMeansEngine(X)
+    with pytest.raises(ValueError):
+        eng.run([(3, np.array([0, 1]))])                 # k rows needed
+    with pytest.raises(ValueError):
+        eng.run([(2, np.array([0, 50]))])                # index out of range
+    with pytest.raises(ValueError):
+        eng.run([(65, np.arange(65) % 50)])              # k <= 64
+    with pytest.raises(NotImplementedError):
+        P.clustering.KMeansLeida(k=2, metric="euclidean").fit(X)
+    with pytest.raises(NotImplementedError):
+        P.signal_tools.get_eigenvectors(np.zeros((4, 4, 3)), n=2)
+
+
+def test_leida_input_validation_and_loader(P, tmp_path):
+    import pickle
+    from pyleida import synthetic
+    ts, classes = synthetic.make_dataset(3, 6, 20, "iid")
+    with pytest.raises(TypeError):
+        P.Leida(123)
+    with pytest.raises(ValueError):
+        P.Leida(str(tmp_path / "missing"))
+    bad = dict(ts)
+    bad["x"] = np.zeros((5, 20))
+    with pytest.raises(Exception):
+        P.Leida.from_arrays(bad, {**classes, "x": ["A"]})
+    (tmp_path / "rois_labels.txt").write_text("\n".join(f"roi {i}" for i in range(6)))
+    pickle.dump(ts, open(tmp_path / "time_series.pkl", "wb"))
+    pickle.dump(classes, open(tmp_path / "metadata.pkl", "wb"))
+    m = P.Leida(str(tmp_path))
+    assert m.rois_labels[0] == "roi 0" and set(m.time_series) == set(ts)
+    with pytest.raises(TypeError):
+        m.fit_predict(TR="fast")
+    with pytest.raises(ValueError):
+        m.fit_predict(n_perm=10)
+    m.fit_predict(TR=2, K_min=2, K_max=3, n_init=1, random_state=0)
+    assert list(m.predictions.columns) == ["subject_id", "condition", "k_2", "k_3"]
+    assert m.load_centroids(3).shape == (6, 3)
