@@ -490,46 +490,101 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
     }
 }
 
-// Distortion: warp per row, fp64 dot with the assigned centroid, exact integer accumulation.
+// Distortion of every run: sum over rows of (1 - cos(row, assigned centroid))^2, fp64 per row,
+// accumulated as exact integers (2^-40 and 2^-80 words) so the result does not depend on the order
+// or on the number of GPUs.  One CTA = 32 rows x all runs: the rows are read ONCE (each warp keeps its
+// row in registers as doubles, lanes stride the columns), the labels of the 32 rows for a chunk of
+// runs are staged in shared memory with coalesced loads, and four runs are in flight per warp.
+constexpr int DIST_ROWS = 32;
+constexpr int DIST_RUN_CHUNK = 256;
+constexpr int DIST_MAX_COLS_PER_LANE = 8;
+
 __global__ void __launch_bounds__(256)
-k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long long M, int N, int XP,
-             const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, const float* __restrict__ cent,
+k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long long M, int N, int XP, int n_runs,
+             const int32_t* __restrict__ run_crow0, const float* __restrict__ cent,
              const double* __restrict__ cnorm, const int32_t* __restrict__ labels, long long* state) {
-    const int run = blockIdx.y;
-    const int crow0 = run_crow0[run];
+    __shared__ int s_lab[DIST_RUN_CHUNK][DIST_ROWS];
+    __shared__ unsigned long long s_hi[DIST_RUN_CHUNK], s_lo[DIST_RUN_CHUNK];
+    __shared__ int s_c0[DIST_RUN_CHUNK];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int32_t* lab = labels + (long long)run * M;
-    long long hi = 0, lo = 0;
-    const long long rows_per_cta = 256;
-    const long long r0 = (long long)blockIdx.x * rows_per_cta;
-    for (long long row = r0 + w; row < r0 + rows_per_cta && row < M; row += 8) {
-        const int l = lab[row];
-        const float* xr = X + row * XP;
-        const float* cr = cent + (long long)(crow0 + (l < 0 ? 0 : l)) * XP;
-        double s = 0.0;
-        for (int j = lane; j < N; j += 32) s += (double)xr[j] * (double)cr[j];
-        s = warp_sum(s);
-        if (lane == 0) {
-            const double d = cosine_distance(s, xnorm[row], cnorm[crow0 + (l < 0 ? 0 : l)]);
-            const double d2 = d * d * kFracScale;   // exact scaling
-            if (d2 == d2) {
-                const double f = floor(d2);
-                hi += (long long)f;
-                lo += (long long)floor((d2 - f) * kFracScale);
-            } else {
-                hi = (long long)0x4000000000000000LL;   // poison: NaN distance (degenerate row / centroid)
+    const long long row0 = (long long)blockIdx.x * DIST_ROWS;
+    const bool in_regs = N <= 32 * DIST_MAX_COLS_PER_LANE;
+    for (int r0 = 0; r0 < n_runs; r0 += DIST_RUN_CHUNK) {
+        const int nr = min(DIST_RUN_CHUNK, n_runs - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * DIST_ROWS; i += 256) {
+            const int r = i >> 5, c = i & 31;
+            const long long row = row0 + c;
+            s_lab[r][c] = row < M ? labels[(long long)(r0 + r) * M + row] : -1;
+        }
+        for (int i = threadIdx.x; i < nr; i += 256) { s_hi[i] = 0; s_lo[i] = 0; s_c0[i] = run_crow0[r0 + i]; }
+        __syncthreads();
+        for (int rr = w; rr < DIST_ROWS; rr += 8) {
+            const long long row = row0 + rr;
+            if (row >= M) break;
+            const float* xr = X + row * XP;
+            const double xn = xnorm[row];
+            double xv[DIST_MAX_COLS_PER_LANE];
+            if (in_regs) {
+#pragma unroll
+                for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) {
+                    const int j = lane + 32 * i;
+                    xv[i] = j < N ? (double)xr[j] : 0.0;
+                }
+            }
+            for (int q0 = 0; q0 < nr; q0 += 4) {
+                double s4[4] = {0.0, 0.0, 0.0, 0.0};
+                int crow[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = min(q0 + u, nr - 1);
+                    const int l = s_lab[r][rr];
+                    crow[u] = s_c0[r] + (l < 0 ? 0 : l);
+                }
+                if (in_regs) {
+                    float cv[4][DIST_MAX_COLS_PER_LANE];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float* cr = cent + (long long)crow[u] * XP;
+#pragma unroll
+                        for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) {
+                            const int j = lane + 32 * i;
+                            cv[u][i] = j < N ? cr[j] : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) s4[u] = fma(xv[i], (double)cv[u][i], s4[u]);
+                } else {
+                    for (int u = 0; u < 4; ++u) {
+                        const float* cr = cent + (long long)crow[u] * XP;
+                        for (int j = lane; j < N; j += 32) s4[u] = fma((double)xr[j], (double)cr[j], s4[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s4[u] = warp_sum(s4[u]);
+                if (lane < 4 && q0 + lane < nr) {
+                    const double sv = lane == 0 ? s4[0] : lane == 1 ? s4[1] : lane == 2 ? s4[2] : s4[3];
+                    const int cr_l = lane == 0 ? crow[0] : lane == 1 ? crow[1] : lane == 2 ? crow[2] : crow[3];
+                    const double d = cosine_distance(sv, xn, cnorm[cr_l]);
+                    const double d2 = d * d * kFracScale;   // exact scaling
+                    if (d2 == d2) {
+                        const double f = floor(d2);
+                        atomicAdd(&s_hi[q0 + lane], (unsigned long long)(long long)f);
+                        atomicAdd(&s_lo[q0 + lane], (unsigned long long)(long long)floor((d2 - f) * kFracScale));
+                    } else {
+                        atomicAdd(&s_hi[q0 + lane], 0x4000000000000000ULL);   // poison: NaN distance
+                    }
+                }
             }
         }
-    }
-    __shared__ long long s_hi[8], s_lo[8];
-    if (lane == 0) { s_hi[w] = hi; s_lo[w] = lo; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long a = 0, b = 0;
-        for (int i = 0; i < 8; ++i) { a += s_hi[i]; b += s_lo[i]; }
-        if (a | b) {
-            atomic_add_ll(state + (long long)run * kStateWords + LEIDA_KM_ST_DIST_HI, a);
-            atomic_add_ll(state + (long long)run * kStateWords + LEIDA_KM_ST_DIST_LO, b);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr; i += 256) {
+            if (s_hi[i] | s_lo[i]) {
+                atomic_add_ll(state + (long long)(r0 + i) * kStateWords + LEIDA_KM_ST_DIST_HI, (long long)s_hi[i]);
+                atomic_add_ll(state + (long long)(r0 + i) * kStateWords + LEIDA_KM_ST_DIST_LO, (long long)s_lo[i]);
+            }
         }
     }
 }
@@ -770,9 +825,8 @@ extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int6
     if (rc) return rc;
     k_zero_dist<<<(n_runs + 127) / 128, 128, 0, st>>>((long long*)state, n_runs);
     if (M > 0) {
-        dim3 grid((unsigned)((M + 255) / 256), (unsigned)n_runs);
-        k_distortion<<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, run_k, run_crow0, cent, cnorm, labels,
-                                           (long long*)state);
+        k_distortion<<<(unsigned)((M + DIST_ROWS - 1) / DIST_ROWS), 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0,
+                                                                                  cent, cnorm, labels, (long long*)state);
     }
     return check_launch("k_distortion", M > 0 ? 2 : 1);
 }
