@@ -532,49 +532,57 @@ k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long
                     xv[i] = j < N ? (double)xr[j] : 0.0;
                 }
             }
-            for (int q0 = 0; q0 < nr; q0 += 4) {
-                double s4[4] = {0.0, 0.0, 0.0, 0.0};
-                int crow[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int r = min(q0 + u, nr - 1);
-                    const int l = s_lab[r][rr];
-                    crow[u] = s_c0[r] + (l < 0 ? 0 : l);
-                }
-                if (in_regs) {
-                    float cv[4][DIST_MAX_COLS_PER_LANE];
+            for (int g0 = 0; g0 < nr; g0 += 32) {
+                // 32 runs per group: lane u ends up holding the dot product of run g0+u, so the fp64
+                // division, the squaring and the shared-memory accumulation use all 32 lanes.
+                double mine = 0.0;
+                int mycrow = 0;
+                const int gend = min(g0 + 32, nr);
+                for (int q0 = g0; q0 < gend; q0 += 4) {
+                    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+                    int crow[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float* cr = cent + (long long)crow[u] * XP;
+                        const int r = min(q0 + u, nr - 1);
+                        const int l = s_lab[r][rr];
+                        crow[u] = s_c0[r] + (l < 0 ? 0 : l);
+                    }
+                    if (in_regs) {
+                        float cv[4][DIST_MAX_COLS_PER_LANE];
 #pragma unroll
-                        for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) {
-                            const int j = lane + 32 * i;
-                            cv[u][i] = j < N ? cr[j] : 0.f;
+                        for (int u = 0; u < 4; ++u) {
+                            const float* cr = cent + (long long)crow[u] * XP;
+#pragma unroll
+                            for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) {
+                                const int j = lane + 32 * i;
+                                cv[u][i] = j < N ? cr[j] : 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) s4[u] = fma(xv[i], (double)cv[u][i], s4[u]);
+                    } else {
+                        for (int u = 0; u < 4; ++u) {
+                            const float* cr = cent + (long long)crow[u] * XP;
+                            for (int j = lane; j < N; j += 32) s4[u] = fma((double)xr[j], (double)cr[j], s4[u]);
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) s4[u] = fma(xv[i], (double)cv[u][i], s4[u]);
-                } else {
                     for (int u = 0; u < 4; ++u) {
-                        const float* cr = cent + (long long)crow[u] * XP;
-                        for (int j = lane; j < N; j += 32) s4[u] = fma((double)xr[j], (double)cr[j], s4[u]);
+                        const double t = warp_sum(s4[u]);
+                        if (lane == q0 - g0 + u) { mine = t; mycrow = crow[u]; }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) s4[u] = warp_sum(s4[u]);
-                if (lane < 4 && q0 + lane < nr) {
-                    const double sv = lane == 0 ? s4[0] : lane == 1 ? s4[1] : lane == 2 ? s4[2] : s4[3];
-                    const int cr_l = lane == 0 ? crow[0] : lane == 1 ? crow[1] : lane == 2 ? crow[2] : crow[3];
-                    const double d = cosine_distance(sv, xn, cnorm[cr_l]);
+                if (g0 + lane < gend) {
+                    const double d = cosine_distance(mine, xn, cnorm[mycrow]);
                     const double d2 = d * d * kFracScale;   // exact scaling
                     if (d2 == d2) {
                         const double f = floor(d2);
-                        atomicAdd(&s_hi[q0 + lane], (unsigned long long)(long long)f);
-                        atomicAdd(&s_lo[q0 + lane], (unsigned long long)(long long)floor((d2 - f) * kFracScale));
+                        atomicAdd(&s_hi[g0 + lane], (unsigned long long)(long long)f);
+                        atomicAdd(&s_lo[g0 + lane], (unsigned long long)(long long)floor((d2 - f) * kFracScale));
                     } else {
-                        atomicAdd(&s_hi[q0 + lane], 0x4000000000000000ULL);   // poison: NaN distance
+                        atomicAdd(&s_hi[g0 + lane], 0x4000000000000000ULL);   // poison: NaN distance
                     }
                 }
             }
