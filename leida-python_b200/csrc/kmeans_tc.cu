@@ -525,15 +525,24 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     if (threadIdx.x == 0) s_n = 0;
     if (threadIdx.x <= LEIDA_KM_MAX_K) { s_cin[threadIdx.x] = 0; s_cout[threadIdx.x] = 0; }
     __syncthreads();
-    for (int r = threadIdx.x; r < APPLY_ROWS; r += APPLY_THREADS) {
-        const long long row = row_base + r;
-        if (row < M) {
-            const int o = cur[row], n = nw[row];
-            if (o != n) {
-                cur[row] = n;
-                s_list[atomicAdd(&s_n, 1)] = r | ((o & 0xff) << 16) | (n << 24);   // r < 4096 < 2^16
-                atomicAdd(&s_cin[n], 1);
-                if (o >= 0) atomicAdd(&s_cout[o], 1);
+    {   // all label loads of the chunk first (independent, coalesced), then the compares
+        constexpr int PER = APPLY_ROWS / APPLY_THREADS;
+        int lo[PER], ln[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const long long row = row_base + threadIdx.x + i * APPLY_THREADS;
+            const bool ok = row < M;
+            lo[i] = ok ? cur[row] : 0;
+            ln[i] = ok ? nw[row] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            if (lo[i] != ln[i]) {
+                const int r = threadIdx.x + i * APPLY_THREADS;       // r < 4096 < 2^16
+                cur[row_base + r] = ln[i];
+                s_list[atomicAdd(&s_n, 1)] = r | ((lo[i] & 0xff) << 16) | (ln[i] << 24);
+                atomicAdd(&s_cin[ln[i]], 1);
+                if (lo[i] >= 0) atomicAdd(&s_cout[lo[i]], 1);
             }
         }
     }
