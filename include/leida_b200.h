@@ -216,8 +216,8 @@ int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_cro
                         float* cent, double* cnorm, int64_t* state, int n_iter,
                         int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
                         int32_t* mailbox, leida_stream_t stream);
-/* n_active_out: device int32[4], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
- * [2] = runs still active after this call).  mailbox (may be NULL): HOST-visible (pinned, mapped)
+/* n_active_out: device int32[8], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
+ * [2] = runs still active after this call, [3] = calls completed, [4] = first all-stopped call).  mailbox (may be NULL): HOST-visible (pinned, mapped)
  * int32[4]; the last CTA stores {runs still active, number of update calls completed, index of the
  * first update call that left no run active (0 = not yet)} there so the host can follow convergence
  * without synchronising or copying.  With several ranks the values are identical on every rank (they

@@ -462,12 +462,15 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             n_active[0] = 0;
             n_active[1] = 0;
             if (mailbox) {
-                const int done = mailbox[1] + 1;
+                // device-side copy of the counters (n_active[3] = passes done, n_active[4] = first all-stopped
+                // pass), published to the host with two plain stores ordered by one system fence
+                const int done = n_active[3] + 1;
+                n_active[3] = done;
+                if (na == 0 && n_active[4] == 0) n_active[4] = done;
                 mailbox[0] = na;
-                if (na == 0 && mailbox[2] == 0) mailbox[2] = done;   // first update call after which no run is active
+                mailbox[2] = n_active[4];
                 __threadfence_system();
                 mailbox[1] = done;
-                __threadfence_system();
             }
         }
     }

@@ -18,7 +18,9 @@ _KP_BUCKETS = (4, 8, 12, 16, 20, 24, 32, 40, 48, 64)
 # 'tc': tcgen05 tensor-core assignment (production path); 'simt': fp32 CUDA-core kernel kept for
 # cross-checking the two implementations against each other in the tests.
 DEFAULT_ASSIGN = os.environ.get("LEIDA_KMEANS_ASSIGN", "tc")
-USE_CUDA_GRAPHS = os.environ.get("LEIDA_CUDA_GRAPHS", "1") != "0"
+# Replaying the pass as a CUDA graph is supported but off by default: the eager loop needs ~50 us of host
+# time per pass and is GPU-bound, while capturing costs tens of ms per run() (measured: tools/runcost.py).
+USE_CUDA_GRAPHS = os.environ.get("LEIDA_CUDA_GRAPHS", "0") != "0"
 
 
 def _bucket(k):
@@ -131,7 +133,7 @@ class KMeansEngine:
         cap = int(min(max(R * self.M // 8, 1 << 16), 1 << 24))    # (run,row) pairs queued for the fp64 re-check per pass
         worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
         worklist[:8].zero_()
-        n_active = torch.zeros(4, dtype=torch.int32, device=dev)
+        n_active = torch.zeros(8, dtype=torch.int32, device=dev)
         mailbox = torch.zeros(4, dtype=torch.int32, pin_memory=True)   # written by the last CTA of leida_kmeans_update
         mb = mailbox.numpy()
         st = nv.stream()
@@ -210,7 +212,7 @@ class KMeansEngine:
                     nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
                     nv.ptr(worklist), cap, nv.ptr(labels_new), stq))
                 timed("apply", lambda: nv.call(
-                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(plan),
+                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(grid_bound[0]), nv.ptr(plan),
                     nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
                     nv.ptr(state), stq))
             if self.comm.world > 1:
@@ -245,12 +247,15 @@ class KMeansEngine:
         mb[:] = 0
         packed_bound = R
         active_bound = R
+        grid_bound = [R]        # upper bound of the packed-run count, sizes the apply grid (eager launches only)
         issued = 0
         graphs = None
         while True:
             if tc and mb[2] == 0 and 0 < active_bound <= 0.9 * packed_bound:
                 tc_plan()                              # re-pack: only the runs still active keep tensor-core columns
                 packed_bound = active_bound
+                if not use_graph:
+                    grid_bound[0] = max(1, packed_bound)
             if use_graph and issued == 1 and not eager_rest:
                 graphs = self._capture(do_assign, do_rest, split=time_assign)
             if graphs is None:
