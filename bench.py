@@ -266,7 +266,7 @@ def native_arm(args):
         return m
 
     for _ in range(args.warmup):
-        step_device()
+        step_device()                                  # result dropped at once: the timed steps reuse its memory
     profile = {"*": True} if os.environ.get("LEIDA_BENCH_PROFILE_ALL") else {"assign": []}
     sampler = ClockSampler(local_rank)
     barrier()
@@ -275,16 +275,26 @@ def native_arm(args):
     l0 = nvl.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    last = None
     graph_launches = 0
+    step_marks = []
+    stats = None
     for _ in range(args.steps):
-        last = step_device(profile)
-        graph_launches += last.batch.graph_launches
+        res = step_device(profile)
+        graph_launches += res.batch.graph_launches
+        b = res.batch
+        stats = dict(run_passes=b.total_passes(), lockstep=b.lockstep_passes, n_runs=len(b._ks),
+                     sum_k_passes=float(sum(b.k(i) * b.passes(i) for i in range(len(b._ks)))),
+                     rechecked=b.rechecked_total, changed=b.changed_total)
+        del res, b                                     # free the step's tensors before the next step allocates
+        m = torch.cuda.Event(enable_timing=True)
+        m.record()
+        step_marks.append(m)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = nvl.launch_count() - l0 + graph_launches     # kernels inside replayed CUDA graphs are counted by the engine
     ms = e0.elapsed_time(e1)
+    per_step_ms = [a.elapsed_time(b) for a, b in zip([e0] + step_marks[:-1], step_marks)]
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     ln = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
@@ -297,7 +307,7 @@ def native_arm(args):
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in profile.items() if k != "*"}
     assign_ms = kernel_ms.get("assign", 0.0)
     n_assign = len(profile.get("assign", []))
-    run_passes = last.batch.total_passes()             # per step (same every step: deterministic)
+    run_passes = stats["run_passes"]                    # per step (same every step: deterministic)
     alg_bytes_per_run_pass = 4.0 * M_local * wl["N"] + 8.0 * M_local
     alg_bytes = alg_bytes_per_run_pass * run_passes * args.steps
     peak, peak_src = measured_peaks()
@@ -305,7 +315,7 @@ def native_arm(args):
     # what the tensor-core kernel really does per launch: one read of the bf16 x 2 split rows for ALL
     # active runs, and 3 bf16 MMAs (X1*C1 + X1*C2 + X2*C1) per output
     npk = (wl["N"] + 63) // 64 * 64
-    sum_k_passes = float(sum(last.batch.k(i) * last.batch.passes(i) for i in range(len(last.batch._ks))))
+    sum_k_passes = stats["sum_k_passes"]
     tensor_flops = 3 * 2.0 * M_local * npk * sum_k_passes * args.steps
     actual_bytes = n_assign * (2 * 2.0 * M_local * npk) + 4.0 * M_local * run_passes * args.steps
     roofline = {"kernel": "k_tc_assign (tcgen05 bf16x3 distance GEMM + top-2 epilogue)", "bound": "hbm",
@@ -322,14 +332,18 @@ def native_arm(args):
                         "a launch really moves (bf16x2 rows once + int32 labels per active run)"}
 
     # end-to-end through the public API from host arrays
-    step_e2e()
+    for _ in range(2):
+        step_e2e()                                     # warm-up (pinned staging buffers, allocator); result dropped
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = max(1, min(args.steps, 5))
     f0.record()
     t_wall = time.perf_counter()
+    h2d = d2h = 0
     for _ in range(n_e2e):
         m = step_e2e()
+        h2d, d2h = int(m.h2d_bytes), int(m.d2h_bytes)
+        del m
     f1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall
@@ -349,12 +363,13 @@ def native_arm(args):
             "data": "synthetic",
             "config": {"workload": wl["name"], "kind": wl["kind"], "subjects_total": S_total, "volumes_total": M_global,
                        "kmeans_runs": len(inits) * wl["n_init"], "kmeans_run_passes_per_step": run_passes,
-                       "lockstep_passes_per_step": last.batch.lockstep_passes,
+                       "lockstep_passes_per_step": stats["lockstep"],
+                       "fp64_rechecks_per_step": stats["rechecked"], "label_changes_per_step": stats["changed"],
                        "init": "explicit init rows from default_rng(0), shared with the CPU arm",
-                       "l2_flush_between_steps": True, "parallelism": f"subjects sharded over {world} GPU(s)"},
+                       "l2_flush_between_steps": True, "per_step_ms": [round(v, 2) for v in per_step_ms], "parallelism": f"subjects sharded over {world} GPU(s)"},
             "roofline": roofline,
-            "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(m.h2d_bytes) * world,
-                    "d2h_bytes_per_step": int(m.d2h_bytes) * world, "steps": n_e2e,
+            "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "steps": n_e2e,
                     "ms_per_step": float(te.item()) / n_e2e},
             "gpu_launches": int(ln.item()),
             "clocks": clocks,
