@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -263,6 +263,10 @@ def native_arm(args):
         m = pyleida.Leida.from_arrays(ts, classes, comm=comm)
         m.fit_predict(TR=wl["TR"], K_min=wl["K_min"], K_max=wl["K_max"], n_init=wl["n_init"], init_indices=inits,
                       keep_eigenvectors=True)
+        # consume the result like a user would: labels of every K are already host arrays; the metric
+        # DataFrames are assembled on access -- touch the three tables of one K
+        k = wl["K_max"]
+        _ = (m.predictions[f"k_{k}"].values[-1], m.occupancies(k).shape, m.dwell_times(k).shape, m.transitions(k).shape)
         return m
 
     for _ in range(args.warmup):
@@ -319,7 +323,13 @@ def native_arm(args):
     tensor_flops = 3 * 2.0 * M_local * npk * sum_k_passes * args.steps
     actual_bytes = n_assign * (2 * 2.0 * M_local * npk) + 4.0 * M_local * run_passes * args.steps
     roofline = {"kernel": "k_tc_assign (tcgen05 bf16x3 distance GEMM + top-2 epilogue)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch that serves all 285 runs of this
+                # workload (ncu --set full, profiles/r01_k_tc_assign_ncu_full.txt capture C: 64.2 MB read =
+                # one pass over the bf16x2 rows, 95.3 MB written = the int32 labels); that launch's algorithmic
+                # bytes on the SURVEY metric are 285 x 56.5 MB = 16.1 GB
+                "traffic": 159.5e6 if (world == 1 and wl["S"] == 100 and wl["N"] == 116) else None,
+                "traffic_launch": "full pass, 285 active runs (captured once with ncu; per-launch traffic shrinks with the active-run count)",
                 "peak_source": peak_src, "launches": n_assign, "avg_launch_ms": assign_ms / max(n_assign, 1),
                 "share_of_step": assign_ms / ms,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_assign, 1),
@@ -376,7 +386,7 @@ def native_arm(args):
         }
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        sample_subjects, n_init_sample = 8, 1
+        sample_subjects, n_init_sample = 16, 2
         times = run_cpu_sample(wl, sample_subjects, n_init_sample, 1, 0, cores)
         cv, _ = cpu_value(times, wl, n_init_sample)
         out["cpu_baseline"] = {

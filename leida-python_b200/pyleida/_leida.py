@@ -197,7 +197,8 @@ class Leida:
         labels = pinned["labels"].numpy()
         occ, runs, trans = pinned["occ"].numpy(), pinned["runs"].numpy(), pinned["trans"].numpy()
         self.d2h_bytes += labels.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
-        predictions = pd.DataFrame({"subject_id": sub_list, "condition": cond_list})
+        predictions = pd.DataFrame({"subject_id": pd.Series(sub_list, dtype=object),
+                                    "condition": pd.Series(cond_list, dtype=object)})
         models, perf = {}, []
         for c, k in enumerate(ks):
             km = res.models[k]
@@ -205,9 +206,9 @@ class Leida:
             km.cluster_centers_ = pinned[f"c{k}"].numpy().copy()
             self.d2h_bytes += km.cluster_centers_.nbytes
             models[f"k_{k}"] = km
-            predictions[f"k_{k}"] = km.labels_
             perf.append({"k": k, "Dunn_score": np.nan, "distortion": km.inertia_, "silhouette_score": np.nan,
                          "Davies-Bouldin_score": np.nan})
+        predictions = pd.concat([predictions, pd.DataFrame(labels.T.astype(np.int64), columns=[f"k_{k}" for k in ks])], axis=1)
         self._lei_host = None
         if keep_eigenvectors:
             self._lei_host = pinned["lei"].numpy()         # stays in the pinned buffer (no second copy)
@@ -232,8 +233,8 @@ class Leida:
             if getattr(self, "_lei_host", None) is None:
                 raise Exception("eigenvectors were not kept (keep_eigenvectors=False) or the model is not fitted")
             df = pd.DataFrame(self._lei_host, columns=self.rois_labels)
-            df.insert(0, "subject_id", self._meta[0])
-            df.insert(1, "condition", self._meta[1])
+            df.insert(0, "subject_id", pd.Series(self._meta[0], dtype=object))
+            df.insert(1, "condition", pd.Series(self._meta[1], dtype=object))
             self._eigenvectors_df = df
         return self._eigenvectors_df
 

@@ -175,13 +175,38 @@ def _group_tables(metadata, labels, segments=None):
 
 
 def _frame(seg, values, cols):
-    """DataFrame(subject_id, condition, *cols) built in one go (column inserts are slow)."""
+    """DataFrame(subject_id, condition, *cols): one numeric block + the two id columns."""
     import pandas as pd
-    data = {"subject_id": seg.subjects_array(), "condition": seg.conditions_array()}
-    values = np.ascontiguousarray(values)
-    for i, c in enumerate(cols):
-        data[c] = values[:, i]
-    return pd.DataFrame(data, copy=False)
+    meta = pd.DataFrame({"subject_id": pd.Series(seg.subjects_array(), dtype=object),
+                         "condition": pd.Series(seg.conditions_array(), dtype=object)})
+    return pd.concat([meta, pd.DataFrame(np.ascontiguousarray(values), columns=cols)], axis=1)
+
+
+class LazyFrames(dict):
+    """{'k_K': DataFrame} whose DataFrames are assembled on first access from the exact integer
+    tables (the arithmetic is already done; pandas object construction is the expensive part)."""
+
+    def __init__(self, builders):
+        super().__init__()
+        self._builders = dict(builders)
+        for k in self._builders:
+            dict.__setitem__(self, k, None)
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if v is None and key in self._builders:
+            v = self._builders.pop(key)()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
 
 
 def _state_frame(seg, values, k):
@@ -246,10 +271,10 @@ def compute_dynamics_metrics(clusters_labels, TR=None, save_results=False, path=
 def tables_from_counts(names, col_k, seg, occ, runs, trans, TR=None):
     """The reference's three DataFrames per K column from the integer tables of dynamics_counts()."""
     lengths = np.diff(seg.off)
-    out = {"dwell_times": {}, "occupancies": {}, "transitions": {}}
+    b_occ, b_dw, b_tr = {}, {}, {}
     for i, name in enumerate(names):
         k = int(col_k[i])
-        out["occupancies"][name] = _state_frame(seg, _occupancy(occ[i][:, :k], lengths), k)
-        out["dwell_times"][name] = _state_frame(seg, _dwell(occ[i][:, :k], runs[i][:, :k], TR), k)
-        out["transitions"][name] = _transition_frame(seg, _transitions(trans[i][:, :k, :k]), k)
-    return out
+        b_occ[name] = lambda i=i, k=k: _state_frame(seg, _occupancy(occ[i][:, :k], lengths), k)
+        b_dw[name] = lambda i=i, k=k: _state_frame(seg, _dwell(occ[i][:, :k], runs[i][:, :k], TR), k)
+        b_tr[name] = lambda i=i, k=k: _transition_frame(seg, _transitions(trans[i][:, :k, :k]), k)
+    return {"dwell_times": LazyFrames(b_dw), "occupancies": LazyFrames(b_occ), "transitions": LazyFrames(b_tr)}

@@ -18,4 +18,4 @@ for rep in range(4):
         pr.disable()
     torch.cuda.synchronize(); t1 = time.perf_counter()
     print(f"rep{rep}: fit_predict {1e3*(t1-t0):.1f} ms  h2d {m.h2d_bytes/1e6:.0f} MB d2h {m.d2h_bytes/1e6:.0f} MB")
-pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+pstats.Stats(pr).sort_stats("tottime").print_stats(18)
