@@ -191,7 +191,7 @@ def reference_arm(args):
         return 0
     wl = WORKLOAD
     cores = os.cpu_count() or 1
-    sample_subjects, n_init_sample = 8, 1
+    sample_subjects, n_init_sample = 16, 2
     times = run_cpu_sample(wl, sample_subjects, n_init_sample, args.steps, args.warmup, cores)
     value, t_equiv = cpu_value(times, wl, n_init_sample)
     sample = (f"oracle port (oracle/leida_oracle.py: numpy/scipy restatement of the reference algorithm, closed-form "
