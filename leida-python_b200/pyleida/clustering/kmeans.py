@@ -127,9 +127,13 @@ class KMeansEngine:
         AP = self.XP + 8
         cent = torch.empty((CR, self.XP), dtype=torch.float32, device=dev)
         cnorm = torch.empty(CR, dtype=torch.float64, device=dev)
-        acc = torch.empty((CR, AP), dtype=torch.int64, device=dev)
+        # acc and the run state live in ONE int64 buffer: with several ranks a pass needs a single copy and a
+        # single all-reduce (only the reducible state words are read from the reduced copy)
+        n_acc = CR * AP
+        red_local = torch.empty(n_acc + R * nv.STATE_WORDS, dtype=torch.int64, device=dev)
+        acc = red_local[:n_acc].view(CR, AP)
+        state = red_local[n_acc:].view(R, nv.STATE_WORDS)
         labels = torch.empty((R, self.M), dtype=torch.int32, device=dev)
-        state = torch.empty((R, nv.STATE_WORDS), dtype=torch.int64, device=dev)
         cap = int(min(max(R * self.M // 8, 1 << 16), 1 << 24))    # (run,row) pairs queued for the fp64 re-check per pass
         worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
         worklist[:8].zero_()
@@ -143,8 +147,9 @@ class KMeansEngine:
             init_idx = torch.arange(CR, dtype=torch.int64, device=dev)
             nv.call("leida_kmeans_init", nv.ptr(seed_rows), self.XP, nv.ptr(init_idx), R, nv.ptr(run_k), nv.ptr(run_c0),
                     self.N, self.XP, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), self.M, nv.ptr(state), st)
-            acc_red = torch.empty_like(acc)
-            state_red = torch.empty_like(state)
+            red_global = torch.empty_like(red_local)
+            acc_red = red_global[:n_acc].view(CR, AP)
+            state_red = red_global[n_acc:].view(R, nv.STATE_WORDS)
         else:
             init_idx = torch.from_numpy(seeds_global).to(dev)
             nv.call("leida_kmeans_init", nv.ptr(self.X), self.XP, nv.ptr(init_idx), R, nv.ptr(run_k), nv.ptr(run_c0),
@@ -216,10 +221,8 @@ class KMeansEngine:
                     nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
                     nv.ptr(state), stq))
             if self.comm.world > 1:
-                acc_red.copy_(acc)
-                state_red.copy_(state)
-                self.comm.all_reduce_sum_(acc_red)
-                self.comm.all_reduce_sum_(state_red)
+                red_global.copy_(red_local)
+                self.comm.all_reduce_sum_(red_global)
             timed("update", lambda: nv.call(
                 "leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
                 nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
@@ -287,10 +290,8 @@ class KMeansEngine:
             nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), st))
         launches += 2
         if self.comm.world > 1:
-            state_red.copy_(state)
-            self.comm.all_reduce_sum_(state_red)
-            acc_red.copy_(acc)
-            self.comm.all_reduce_sum_(acc_red)
+            red_global.copy_(red_local)
+            self.comm.all_reduce_sum_(red_global)
             dist_words = state_red[:, [nv.ST_DIST_HI, nv.ST_DIST_LO]].cpu().numpy()
         else:
             dist_words = state[:, [nv.ST_DIST_HI, nv.ST_DIST_LO]].cpu().numpy()
