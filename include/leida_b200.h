@@ -252,6 +252,29 @@ int leida_kmeans_transform_f64(const float* X, int64_t M, int N, int64_t x_pitch
 int leida_remap_labels_i32(int32_t* labels, int64_t M, const int32_t* lut, int K, leida_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Clustering quality scores of identify_states (clustering/_clustering.py:331-339, dunn_fast :934-973;
+ * sklearn silhouette_score(metric='cosine'), davies_bouldin_score)  -- SURVEY 8f-1.
+ * All label columns (one per K) are scored in one call.  labels: int32 (n_cols, label_pitch) over ALL
+ * rows; sel (device int64, n entries, may be NULL = the first n rows) picks the scored sub-sample
+ * (the reference scores 30 000 random rows when M > 30 000, :318-320).  col0[c] = first cluster slot
+ * of column c (slots are col_k[c] wide, total_clusters in all).
+ * leida_scores_cosine: xs float (n, x_pitch) scratch; G int64 (total_clusters, x_pitch) and cnt
+ *   int32 (total_clusters) receive the fixed-point (2^40) sums of the normalised rows per cluster and
+ *   the cluster sizes; outputs per column: sil_sum int64 = sum_i silhouette_i * 2^40,
+ *   min_inter / max_intra uint32 = float bits of the smallest non-zero inter-cluster and the largest
+ *   intra-cluster cosine distance (Dunn = min_inter / max_intra).
+ * leida_scores_db: centroids double (total_clusters, N); dist_sum int64 (total_clusters) = sum over the
+ *   members of the Euclidean distance to their centroid * 2^40.
+ * ------------------------------------------------------------------------------------------ */
+int leida_scores_cosine(const float* X, int64_t x_pitch, int N, const int64_t* sel, int64_t n,
+                        const int32_t* labels, int64_t label_pitch, int n_cols, const int32_t* col0,
+                        const int32_t* col_k, int total_clusters, float* xs, int64_t* G, int32_t* cnt,
+                        int64_t* sil_sum, uint32_t* min_inter, uint32_t* max_intra, leida_stream_t stream);
+int leida_scores_db(const float* X, int64_t x_pitch, int N, int64_t M, const int32_t* labels,
+                    int64_t label_pitch, int n_cols, const int32_t* col0, const double* centroids,
+                    int total_clusters, int64_t* dist_sum, leida_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage 4 -- dynamics metrics counts
  *   (dynamics_metrics/_dynamics_metrics.py:131-134 occupancy, :447-453 runs, :242-245 transitions)
  * labels: int32 (n_cols, M) with pitch label_pitch; column c uses K = col_k[c] states.

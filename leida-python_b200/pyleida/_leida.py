@@ -102,10 +102,12 @@ class Leida:
     # ------------------------------------------------------------------------------------------
     def fit_predict(self, TR=None, paired_tests=False, n_perm=5_000, save_results=False, random_state=None,
                     K_min=2, K_max=20, n_init=15, init_indices=None, centroid_update="exact",
-                    keep_eigenvectors=True, _profile=None):
+                    keep_eigenvectors=True, scores=True, _profile=None):
         """_leida.py:111-192.  K range and n_init are arguments here (the reference hard-codes
         2..20 and 15, :156-157 / _clustering.py:250); paired_tests / n_perm are validated like the
-        reference but the statistics stage is not run; save_results=True is not supported."""
+        reference but the statistics stage is not run; save_results=True is not supported.  scores=True
+        fills the Dunn / silhouette / Davies-Bouldin columns of the performance table like the reference
+        (they are not part of the benchmarked hot path; single-GPU only)."""
         if TR is not None and not isinstance(TR, (int, float)):
             raise TypeError("'TR' must be 'None', and integer or a floating number!")
         if not isinstance(paired_tests, bool):
@@ -119,11 +121,12 @@ class Leida:
         if save_results:
             warnings.warn("save_results=True: the results folder (SURVEY 8f-3) is not written by the GPU path")
         self._K_min_, self._K_max_ = int(K_min), int(K_max)
-        self._execute_all(TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, _profile)
+        self._execute_all(TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, _profile, scores)
         self._is_fitted = True
         return self
 
-    def _execute_all(self, TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, profile=None):
+    def _execute_all(self, TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, profile=None,
+                     scores=True):
         import pandas as pd
         torch = nv.require_cuda()
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -197,6 +200,14 @@ class Leida:
         labels = pinned["labels"].numpy()
         occ, runs, trans = pinned["occ"].numpy(), pinned["runs"].numpy(), pinned["trans"].numpy()
         self.d2h_bytes += labels.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
+        sc = None
+        if scores and comm.world == 1:                     # Dunn / silhouette / Davies-Bouldin (_clustering.py:331-339)
+            from .clustering.kmeans import score_sample, sweep_runs
+            from .clustering.scores import clustering_scores
+            sc = clustering_scores(res.engine, res.labels, ks, [res.models[k]._centers_exact() for k in ks],
+                                   score_sample(res.engine.M, sweep_runs.last_sample))
+        elif scores:
+            warnings.warn("clustering scores are computed on single-GPU runs only; reporting NaN")
         predictions = pd.DataFrame({"subject_id": pd.Series(sub_list, dtype=object),
                                     "condition": pd.Series(cond_list, dtype=object)})
         models, perf = {}, []
@@ -206,8 +217,9 @@ class Leida:
             km.cluster_centers_ = pinned[f"c{k}"].numpy().copy()
             self.d2h_bytes += km.cluster_centers_.nbytes
             models[f"k_{k}"] = km
-            perf.append({"k": k, "Dunn_score": np.nan, "distortion": km.inertia_, "silhouette_score": np.nan,
-                         "Davies-Bouldin_score": np.nan})
+            perf.append({"k": k, "Dunn_score": sc["Dunn_score"][c] if sc else np.nan, "distortion": km.inertia_,
+                         "silhouette_score": sc["silhouette_score"][c] if sc else np.nan,
+                         "Davies-Bouldin_score": sc["Davies-Bouldin_score"][c] if sc else np.nan})
         predictions = pd.concat([predictions, pd.DataFrame(labels.T.astype(np.int64), columns=[f"k_{k}" for k in ks])], axis=1)
         self._lei_host = None
         if keep_eigenvectors:

@@ -56,6 +56,8 @@ SIGNATURES = {
     "leida_kmeans_means_f32_sequential": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_transform_f64": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, _P, _P]),
     "leida_remap_labels_i32": (c_int, [_P, c_int64, _P, c_int, _P]),
+    "leida_scores_cosine": (c_int, [_P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "leida_scores_db": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P]),
     "leida_dynamics_counts_i32": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
 }
 

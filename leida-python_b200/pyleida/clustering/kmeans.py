@@ -311,6 +311,7 @@ class KMeansEngine:
         out.changed_total = int(st_host[:, nv.ST_CHANGED_TOTAL].sum())
         out.assign = assign
         out.graph_launches = graph_launches
+        out._acc = acc_red                    # exact fixed-point member sums (device), for centers_exact()
         return out
 
     def predict(self, centers):
@@ -351,6 +352,14 @@ class BatchResult:
 
     def labels_device(self, i):
         return self._labels[int(self._inv[i])]
+
+    def centers_exact(self, i):
+        """(K, N) float64 member means of run i from the fixed-point sums (empty clusters -> NaN)."""
+        j = self._inv[i]
+        a, b = int(self._crow0[j]), int(self._crow0[j] + self._ks[j])
+        sums = self._acc[a:b, :self.engine.N].cpu().numpy().astype(np.float64) * 2.0 ** -nv.LEIDA_KM_FRAC_BITS
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return sums / self._counts[a:b].astype(np.float64)[:, None]
 
 
 def _remap_permutation(counts):
@@ -461,6 +470,7 @@ class KMeansLeida:
         nv.call("leida_remap_labels_i32", nv.ptr(lab), lab.numel(), nv.ptr(lut_d), len(lut), nv.stream())
         self.labels_device_ = lab
         self.centers_device_ = res.centers_device(r)[torch.from_numpy(np.ascontiguousarray(order)).to(lab.device)]
+        self._centers_exact = lambda: res.centers_exact(r)[order, :]
         if to_host:
             self.labels_ = lab.cpu().numpy().astype(np.int64)
             self.cluster_centers_ = self.centers_device_.cpu().numpy()
@@ -493,14 +503,25 @@ class KMeansLeida:
         return eng.predict(self.cluster_centers_).cpu().numpy().astype(np.int64)
 
 
+def score_sample(M, drawn=None):
+    """Rows scored by Dunn / silhouette: all of them up to 30 000, else the reference's 30 000-row random
+    sub-sample (clustering/_clustering.py:318-320) -- `drawn` when the draw was already made."""
+    if M <= 30_000:
+        # the reference's two tests (N_samples>30_000 to draw, N_samples<30_000 to use everything) leave
+        # M == 30 000 undefined (NameError); everything is scored here
+        return None
+    return drawn if drawn is not None else np.random.choice(np.arange(M), size=30_000, replace=False)
+
+
 def sweep_runs(M, K_min, K_max, n_init, random_state=None, init_indices=None):
     """The (K, initial rows) runs of a K sweep in the reference's draw order (clustering/_clustering.py:
     318-329), identical restarts removed.  Returns (runs, plan): plan[k][r] = index into runs of
     restart r of K=k."""
+    sweep_runs.last_sample = None
     if M > 30_000 and init_indices is None:
         # :318-320 -- the reference draws its score sub-sample here; repeating the draw keeps the
         # global RNG stream (and therefore every later initial centroid) aligned with it.
-        np.random.choice(np.arange(M), size=30_000, replace=False)
+        sweep_runs.last_sample = np.random.choice(np.arange(M), size=30_000, replace=False)
     runs, plan = [], {}
     for k in range(K_min, K_max + 1):                                          # :326
         inits = list(init_indices[k]) if init_indices is not None else _draw_inits(M, k, n_init, random_state)
@@ -525,14 +546,14 @@ def select_models(engine, res, plan, n_init, to_host=True):
 
 
 def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=None, plot=True, save_results=False,
-                    path=None, init_indices=None, centroid_update="exact", engine=None, scores=False):
+                    path=None, init_indices=None, centroid_update="exact", engine=None, scores=True):
     """K sweep of clustering/_clustering.py:250-374 with every (K, restart) run advanced in
     lock-step on the GPU.  Returns (predictions, clustering_performance, models) like the reference.
 
     eigens_dataset: DataFrame with 'subject_id', 'condition' and one column per ROI (the reference's
     input), or a (metadata DataFrame, KMeansEngine) pair through `engine` to reuse device data.
-    The Dunn / silhouette / Davies-Bouldin columns (:331-339) are outside the accelerated path
-     and are reported as NaN; `plot` is accepted and ignored (no plotting stack).
+    scores=True computes the Dunn / silhouette / Davies-Bouldin columns (:331-339) on the GPU
+    (clustering/scores.py; single-GPU engines only, NaN otherwise); `plot` is accepted and ignored.
     init_indices: optional {k: [idx_r ...]} replacing the legacy-RNG draws.
     """
     import pandas as pd
@@ -545,12 +566,23 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
     runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices)
     res = engine.run(runs, n_iter=1_000, centroid_update=centroid_update)
     by_k = select_models(engine, res, plan, n_init)
+    ks = list(range(K_min, K_max + 1))
+    sc = None
+    if scores and engine.comm.world == 1:
+        from .scores import clustering_scores
+        torch = engine.torch
+        sc = clustering_scores(engine, torch.stack([by_k[k].labels_device_ for k in ks]), ks,
+                               [by_k[k]._centers_exact() for k in ks],
+                               score_sample(engine.M, sweep_runs.last_sample))
+    elif scores:
+        warnings.warn("clustering scores are computed on single-GPU engines only; reporting NaN")
     models, perf = {}, []
-    for k in range(K_min, K_max + 1):
+    for c, k in enumerate(ks):
         km = by_k[k]
         models[f"k_{k}"] = km
-        perf.append({"k": k, "Dunn_score": np.nan, "distortion": km.inertia_, "silhouette_score": np.nan,
-                     "Davies-Bouldin_score": np.nan})
+        perf.append({"k": k, "Dunn_score": sc["Dunn_score"][c] if sc else np.nan, "distortion": km.inertia_,
+                     "silhouette_score": sc["silhouette_score"][c] if sc else np.nan,
+                     "Davies-Bouldin_score": sc["Davies-Bouldin_score"][c] if sc else np.nan})
         meta[f"k_{k}"] = km.labels_                                            # :342
     identify_states.last_batch = res
     return meta, pd.DataFrame(perf), models

@@ -1,0 +1,62 @@
+"""Clustering quality scores on the GPU (reference: pyleida/clustering/_clustering.py:331-339 and
+dunn_fast :934-973; sklearn silhouette_score(metric='cosine') and davies_bouldin_score).
+
+All K columns are scored together: the silhouette through per-cluster sums of the normalised rows
+(no n^2 pass), Dunn through one tiled pairwise pass shared by every K, Davies-Bouldin from the exact
+centroids that k-means already holds.  Only K x K sized arithmetic stays on the host.
+"""
+import numpy as np
+
+from .. import _native as nv
+
+
+def clustering_scores(engine, labels, ks, centroids64, sample_idx=None):
+    """engine: KMeansEngine (rows on the device); labels: CUDA int32 (n_cols, M) final (remapped)
+    labels; ks[c] = K of column c; centroids64[c]: (K, N) float64 exact member means of column c;
+    sample_idx: rows scored by Dunn / silhouette (None = all).  Davies-Bouldin always uses every row,
+    like the reference.  Returns dict of three float64 arrays (n_cols)."""
+    torch = nv.require_cuda()
+    dev = engine.X.device
+    n_cols = len(ks)
+    col_k = np.asarray(ks, dtype=np.int32)
+    col0 = np.zeros(n_cols, dtype=np.int32)
+    col0[1:] = np.cumsum(col_k[:-1])
+    total = int(col_k.sum())
+    labels = labels.to(torch.int32).contiguous()
+    M, N, XP = engine.M, engine.N, engine.XP
+    n = M if sample_idx is None else len(sample_idx)
+    sel = None if sample_idx is None else torch.from_numpy(np.ascontiguousarray(sample_idx, dtype=np.int64)).to(dev)
+    d_col0, d_colk = torch.from_numpy(col0).to(dev), torch.from_numpy(col_k).to(dev)
+    xs = torch.empty((n, XP), dtype=torch.float32, device=dev)
+    G = torch.empty((total, XP), dtype=torch.int64, device=dev)
+    cnt = torch.empty(total, dtype=torch.int32, device=dev)
+    sil = torch.empty(n_cols, dtype=torch.int64, device=dev)
+    mn = torch.empty(n_cols, dtype=torch.int32, device=dev)
+    mx = torch.empty(n_cols, dtype=torch.int32, device=dev)
+    nv.call("leida_scores_cosine", nv.ptr(engine.X), XP, N, nv.ptr(sel), n, nv.ptr(labels), M, n_cols, nv.ptr(d_col0),
+            nv.ptr(d_colk), total, nv.ptr(xs), nv.ptr(G), nv.ptr(cnt), nv.ptr(sil), nv.ptr(mn), nv.ptr(mx), nv.stream())
+    cents = torch.from_numpy(np.ascontiguousarray(np.vstack(centroids64), dtype=np.float64)).to(dev)
+    dsum = torch.empty(total, dtype=torch.int64, device=dev)
+    nv.call("leida_scores_db", nv.ptr(engine.X), XP, N, M, nv.ptr(labels), M, n_cols, nv.ptr(d_col0), nv.ptr(cents), total,
+            nv.ptr(dsum), nv.stream())
+    sil_h = sil.cpu().numpy().astype(np.float64) * 2.0 ** -40 / n
+    mn_h = mn.cpu().numpy().view(np.float32).astype(np.float64)
+    mx_h = mx.cpu().numpy().view(np.float32).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dunn = mn_h / mx_h                                       # np.min(deltas) / np.max(big_deltas)   (:958)
+    dsum_h = dsum.cpu().numpy().astype(np.float64) * 2.0 ** -40
+    db = np.empty(n_cols)
+    for c in range(n_cols):
+        K = int(col_k[c])
+        counts = torch.bincount(labels[c].long(), minlength=K)[:K].cpu().numpy().astype(np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            intra = dsum_h[col0[c]:col0[c] + K] / counts           # mean distance of the members to their centroid
+        cen = np.asarray(centroids64[c], dtype=np.float64)
+        diff = cen[:, None, :] - cen[None, :, :]
+        cd = np.sqrt((diff * diff).sum(-1))                      # pairwise_distances(centroids)
+        if np.allclose(intra, 0) or np.allclose(cd, 0):
+            db[c] = 0.0
+            continue
+        cd[cd == 0] = np.inf
+        db[c] = np.mean(np.max((intra[:, None] + intra[None, :]) / cd, axis=1))
+    return {"Dunn_score": dunn, "silhouette_score": sil_h, "Davies-Bouldin_score": db}

@@ -141,6 +141,10 @@ def pipeline_case():
                                              plot=False, save_results=False)
     dyn = ref.compute_dynamics_metrics(pred, TR=0.72, save_results=False)
     out = dict(S=np.int64(S), N=np.int64(N), T=np.int64(T), lei=lei,
+               perf_k=perf["k"].values.astype(np.int64), perf_dunn=perf["Dunn_score"].values.astype(np.float64),
+               perf_distortion=perf["distortion"].values.astype(np.float64),
+               perf_silhouette=perf["silhouette_score"].values.astype(np.float64),
+               perf_db=perf["Davies-Bouldin_score"].values.astype(np.float64),
                subject_id=np.array(subs), condition=np.array(conds))
     for k in range(2, 7):
         out[f"labels_k{k}"] = pred[f"k_{k}"].values.astype(np.int64)

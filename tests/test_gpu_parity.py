@@ -418,3 +418,46 @@ def test_leida_input_validation_and_loader(P, tmp_path):
     m.fit_predict(TR=2, K_min=2, K_max=3, n_init=1, random_state=0)
     assert list(m.predictions.columns) == ["subject_id", "condition", "k_2", "k_3"]
     assert m.load_centroids(3).shape == (6, 3)
+
+
+# ---- clustering quality scores ----------------------------------------------------
+def test_identify_states_scores_golden(P):
+    """identify_states' performance table (Dunn, distortion, silhouette, Davies-Bouldin) against the
+    table the unmodified reference produced (tests/golden/pipeline_case.npz)."""
+    import pandas as pd
+    g = np.load(os.path.join(GOLD, "pipeline_case.npz"))
+    df = pd.DataFrame(g["lei"], columns=[f"roi{j}" for j in range(int(g["N"]))])
+    df.insert(0, "subject_id", g["subject_id"])
+    df.insert(1, "condition", g["condition"])
+    pred, perf, models = P.clustering.identify_states(df, K_min=2, K_max=6, n_init=3, random_state=0, plot=False)
+    assert list(perf.columns) == ["k", "Dunn_score", "distortion", "silhouette_score", "Davies-Bouldin_score"]
+    assert np.array_equal(perf["k"].values, g["perf_k"])
+    for k in range(2, 7):
+        assert np.array_equal(pred[f"k_{k}"].values, g[f"labels_k{k}"])
+    np.testing.assert_allclose(perf["distortion"].values, g["perf_distortion"], rtol=1e-6)
+    # Dunn is a ratio of single float32 distances (sklearn computes them with BLAS): 1e-4 is the noise floor
+    np.testing.assert_allclose(perf["Dunn_score"].values, g["perf_dunn"], rtol=2e-4)
+    np.testing.assert_allclose(perf["silhouette_score"].values, g["perf_silhouette"], atol=2e-6)
+    np.testing.assert_allclose(perf["Davies-Bouldin_score"].values, g["perf_db"], rtol=1e-5)
+
+
+def test_scores_subsample_and_many_k_vs_oracle(P, O):
+    rng = np.random.default_rng(11)
+    M, N = 6000, 33
+    cent = rng.standard_normal((5, N))
+    X = (cent[rng.integers(0, 5, M)] + 0.9 * rng.standard_normal((M, N))).astype(np.float32)
+    eng = P.clustering.KMeansEngine(X)
+    ks = [2, 3, 7, 12]
+    import torch
+    labs = [rng.integers(0, k, M).astype(np.int32) for k in ks]
+    for lab, k in zip(labs, ks):
+        lab[:k] = np.arange(k)                      # every cluster present
+    cents = [np.vstack([X[lab == c].astype(np.float64).mean(0) for c in range(k)]) for lab, k in zip(labs, ks)]
+    sel = np.sort(rng.choice(M, 2500, replace=False))
+    dev_labels = torch.from_numpy(np.stack(labs)).cuda()
+    got = P.clustering.clustering_scores(eng, dev_labels, ks, cents, sample_idx=sel)
+    for c, (lab, k) in enumerate(zip(labs, ks)):
+        ref = O.clustering_scores(X, lab, sample_idx=sel)
+        assert got["Dunn_score"][c] == pytest.approx(ref["Dunn_score"], rel=2e-4)
+        assert got["silhouette_score"][c] == pytest.approx(ref["silhouette_score"], abs=2e-6)
+        assert got["Davies-Bouldin_score"][c] == pytest.approx(ref["Davies-Bouldin_score"], rel=1e-5)

@@ -103,3 +103,13 @@ def test_pipeline_matches_reference():
         for m in ("occupancies", "dwell_times", "transitions"):
             assert np.array_equal(res["metrics"][k][m], g[f"{m}_k{k}"]), (k, m)
         assert [s for s, _ in res["metrics"][k]["rows"]] == list(g[f"occupancies_k{k}_subject"])
+
+
+def test_clustering_scores_match_reference_table():
+    g = np.load(os.path.join(GOLD, "pipeline_case.npz"))
+    X = g["lei"].astype(np.float32)
+    for i, k in enumerate(g["perf_k"]):
+        sc = O.clustering_scores(X, g[f"labels_k{k}"])
+        assert sc["Dunn_score"] == pytest.approx(g["perf_dunn"][i], rel=1e-6)
+        assert sc["silhouette_score"] == pytest.approx(g["perf_silhouette"][i], abs=1e-6)
+        assert sc["Davies-Bouldin_score"] == pytest.approx(g["perf_db"][i], rel=1e-9)
