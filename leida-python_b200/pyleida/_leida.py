@@ -105,7 +105,8 @@ class Leida:
                     keep_eigenvectors=True, scores=True, _profile=None):
         """_leida.py:111-192.  K range and n_init are arguments here (the reference hard-codes
         2..20 and 15, :156-157 / _clustering.py:250); paired_tests / n_perm are validated like the
-        reference but the statistics stage is not run; save_results=True is not supported.  scores=True
+        reference but the statistics stage is not run; save_results=True writes the reference's
+        'LEiDA_results' folder layout (results_io.py) and, like the reference, refuses to overwrite it.  scores=True
         fills the Dunn / silhouette / Davies-Bouldin columns of the performance table like the reference
         (they are not part of the benchmarked hot path; single-GPU only)."""
         if TR is not None and not isinstance(TR, (int, float)):
@@ -118,11 +119,24 @@ class Leida:
             raise ValueError("The number of permutations cannot be lower than 100.")
         if not isinstance(save_results, bool):
             raise TypeError("'save_results' must be a boolean value (True or False)!")
+        self._results_path_ = "LEiDA_results"
         if save_results:
-            warnings.warn("save_results=True: the results folder (SURVEY 8f-3) is not written by the GPU path")
+            if os.path.exists(self._results_path_):                                        # _leida.py:256-260
+                raise Warning("EXECUTION ABORTED: The folder 'LEiDA_results' already exists. If you have results from "
+                              "earlier executions of the analysis, consider changing the folder's name or moving the "
+                              "folder to another location.")
+            if not keep_eigenvectors:
+                raise ValueError("save_results=True needs keep_eigenvectors=True")
         self._K_min_, self._K_max_ = int(K_min), int(K_max)
         self._execute_all(TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, _profile, scores)
         self._is_fitted = True
+        if save_results:                                                                   # _leida.py:306-310 and the stage writers
+            from .results_io import save_clustering, save_dynamics, save_eigenvectors
+            save_eigenvectors(self._results_path_, self.eigenvectors)
+            save_clustering(self._results_path_, self.predictions, self._clustering_.performance, self._clustering_.models)
+            save_dynamics(self._results_path_, {"occupancies": self._dynamics_.occupancies,
+                                                "dwell_times": self._dynamics_.dwell_times,
+                                                "transitions": self._dynamics_.transitions})
         return self
 
     def _execute_all(self, TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, profile=None,

@@ -480,6 +480,11 @@ class KMeansLeida:
         self.best_init_ = best_init
         self._is_fitted = True
 
+    def __getstate__(self):
+        """Pickle like the reference's models (clustering/_clustering.py:345-350): host attributes only."""
+        drop = ("labels_device_", "centers_device_", "_centers_exact")
+        return {k: v for k, v in self.__dict__.items() if k not in drop}
+
     def _check_is_fitted(self):
         if not hasattr(self, "_is_fitted"):
             raise Exception("You have to fit the model first by using the 'fit' method.")
@@ -557,8 +562,8 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
     init_indices: optional {k: [idx_r ...]} replacing the legacy-RNG draws.
     """
     import pandas as pd
-    if save_results:
-        raise NotImplementedError("results I/O (SURVEY 8f-3) is not part of the accelerated path")
+    if save_results and path is None:
+        raise ValueError("You must provide a path to save the results")
     meta = eigens_dataset[["subject_id", "condition"]].copy()
     if engine is None:
         X = np.array(eigens_dataset.iloc[:, 2:], dtype=np.float32)            # :316
@@ -585,4 +590,8 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
                      "Davies-Bouldin_score": sc["Davies-Bouldin_score"][c] if sc else np.nan})
         meta[f"k_{k}"] = km.labels_                                            # :342
     identify_states.last_batch = res
-    return meta, pd.DataFrame(perf), models
+    perf = pd.DataFrame(perf)
+    if save_results:
+        from ..results_io import save_clustering
+        save_clustering(path, meta, perf, models)
+    return meta, perf, models

@@ -217,30 +217,32 @@ def _transition_frame(seg, values, k):
     return _frame(seg, values.reshape(len(seg), k * k), [f"From_{i + 1}_to_{j + 1}" for i in range(k) for j in range(k)])
 
 
-def _no_io(save_results):
+def _save_one(save_results, path, table, fname):
     if save_results:
-        raise NotImplementedError("results I/O (SURVEY 8f-3) is not part of the accelerated path")
+        if path is None:
+            raise ValueError("You must provide a path to save the results")
+        import os
+        os.makedirs(path, exist_ok=True)
+        table.to_csv(os.path.join(path, fname), sep="\t", index=False)
+    return table
 
 
 def fractional_occupancy_group(metadata, labels, save_results=False, path=None, _segments=None):
     """:138-206."""
-    _no_io(save_results)
     seg, k, occ, _, _ = _group_tables(metadata, labels, _segments)
-    return _state_frame(seg, _occupancy(occ, np.diff(seg.off)), k)
+    return _save_one(save_results, path, _state_frame(seg, _occupancy(occ, np.diff(seg.off)), k), "occupancies.csv")
 
 
 def dwell_times_group(metadata, labels, TR=None, save_results=False, path=None, _segments=None):
     """:475-542."""
-    _no_io(save_results)
     seg, k, occ, runs, _ = _group_tables(metadata, labels, _segments)
-    return _state_frame(seg, _dwell(occ, runs, TR), k)
+    return _save_one(save_results, path, _state_frame(seg, _dwell(occ, runs, TR), k), "dwell_times.csv")
 
 
 def transition_probabilities_group(metadata, labels, save_results=False, path=None, _segments=None):
     """:278-342."""
-    _no_io(save_results)
     seg, k, _, _, trans = _group_tables(metadata, labels, _segments)
-    return _transition_frame(seg, _transitions(trans), k)
+    return _save_one(save_results, path, _transition_frame(seg, _transitions(trans), k), "transitions_probabilities.csv")
 
 
 def compute_dynamics_metrics(clusters_labels, TR=None, save_results=False, path=None, _segments=None,
@@ -249,7 +251,8 @@ def compute_dynamics_metrics(clusters_labels, TR=None, save_results=False, path=
     from ONE GPU launch over all columns.  Returns {'dwell_times','occupancies','transitions'} ->
     {'k_K': DataFrame}.  _device_labels: optional (n_cols, M) CUDA int32 tensor holding the same
     labels as the DataFrame columns (avoids the host round trip inside the pipeline)."""
-    _no_io(save_results)
+    if save_results and path is None:
+        raise ValueError("You must provide a path to save the results")
     if "subject_id" not in clusters_labels.columns:                                       # :58-61
         clusters_labels.rename(columns={clusters_labels.columns[0]: "subject_id"}, inplace=True)
     if "condition" not in clusters_labels.columns:
@@ -265,7 +268,11 @@ def compute_dynamics_metrics(clusters_labels, TR=None, save_results=False, path=
         col_k.append(len(u))
     lab = _device_labels if _device_labels is not None else np.ascontiguousarray(ys.T, dtype=np.int32)
     occ, runs, trans = dynamics_counts(lab, col_k, seg)
-    return tables_from_counts(Ks, col_k, seg, occ, runs, trans, TR)
+    out = tables_from_counts(Ks, col_k, seg, occ, runs, trans, TR)
+    if save_results:
+        from ..results_io import save_dynamics
+        save_dynamics(path, out)
+    return out
 
 
 def tables_from_counts(names, col_k, seg, occ, runs, trans, TR=None):

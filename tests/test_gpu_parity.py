@@ -461,3 +461,30 @@ def test_scores_subsample_and_many_k_vs_oracle(P, O):
         assert got["Dunn_score"][c] == pytest.approx(ref["Dunn_score"], rel=2e-4)
         assert got["silhouette_score"][c] == pytest.approx(ref["silhouette_score"], abs=2e-6)
         assert got["Davies-Bouldin_score"][c] == pytest.approx(ref["Davies-Bouldin_score"], rel=1e-5)
+
+
+def test_results_folder_layout(P, tmp_path, monkeypatch):
+    """save_results=True writes the reference's LEiDA_results layout and refuses to overwrite it."""
+    import pickle
+    import pandas as pd
+    from pyleida import synthetic
+    monkeypatch.chdir(tmp_path)
+    ts, classes = synthetic.make_dataset(4, 8, 30, "states")
+    m = P.Leida.from_arrays(ts, classes).fit_predict(TR=1.0, save_results=True, random_state=0, K_min=2, K_max=3, n_init=1)
+    root = tmp_path / "LEiDA_results"
+    eig = pd.read_csv(root / "eigenvectors.csv", sep="\t")
+    assert list(eig.columns[:2]) == ["subject_id", "condition"] and eig.shape == (4 * 28, 10)
+    np.testing.assert_allclose(eig.iloc[:, 2:].values, m.eigenvectors.iloc[:, 2:].values.astype(float), rtol=0, atol=1e-15)
+    pred = pd.read_csv(root / "clustering" / "predictions.csv", sep="\t")
+    assert np.array_equal(pred["k_3"].values, m.predictions["k_3"].values)
+    perf = pd.read_csv(root / "clustering" / "clustering_performance.csv", sep="\t")
+    assert list(perf.columns) == ["k", "Dunn_score", "distortion", "silhouette_score", "Davies-Bouldin_score"]
+    model = pickle.load(open(root / "clustering" / "models" / "model_k_2.pkl", "rb"))
+    assert np.array_equal(model.cluster_centers_, m.load_model(2).cluster_centers_)
+    for k in (2, 3):
+        for f in ("occupancies.csv", "dwell_times.csv", "transitions_probabilities.csv"):
+            assert (root / "dynamics_metrics" / f"k_{k}" / f).exists()
+    occ = pd.read_csv(root / "dynamics_metrics" / "k_3" / "occupancies.csv", sep="\t")
+    np.testing.assert_allclose(occ.iloc[:, 2:].values, m.occupancies(3).iloc[:, 2:].values.astype(float), atol=1e-15)
+    with pytest.raises(Warning):
+        P.Leida.from_arrays(ts, classes).fit_predict(TR=1.0, save_results=True, K_min=2, K_max=2, n_init=1)
