@@ -278,6 +278,22 @@ class Leida:
         c = self._clustering_.models[f"k_{k}"].cluster_centers_
         return pd.DataFrame(c.T, columns=[f"PL_state_{i + 1}" for i in range(c.shape[0])], index=self.rois_labels)
 
+    def centroids_distances(self, k=2):
+        """Distance of every eigenvector to every centroid of partition k (_leida.py:447-473): DataFrame
+        (subject_id, condition, centroid_1..k), fp64 cosine distances computed on the device rows."""
+        import pandas as pd
+        self._check_is_fitted()
+        if not isinstance(k, int):
+            raise TypeError("'k' must be a integer!")
+        if k not in range(self._K_min_, self._K_max_ + 1):
+            raise ValueError(f"'k' must be a fitted model: you selected 'k'= {k}, but K-Means models were fitted "
+                             f"for the {self._K_min_} - {self._K_max_} range.")
+        d = self.load_model(k).transform(self.device_result_.engine)
+        out = pd.DataFrame(d, columns=[f"centroid_{c + 1}" for c in range(k)])
+        out.insert(0, "subject_id", pd.Series(self._meta[0], dtype=object))
+        out.insert(1, "condition", pd.Series(self._meta[1], dtype=object))
+        return out
+
     def dwell_times(self, k=2):
         self._check_is_fitted()
         return self._dynamics_.dwell_times[f"k_{k}"]

@@ -595,3 +595,41 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
         from ..results_io import save_clustering
         save_clustering(path, meta, perf, models)
     return meta, perf, models
+
+
+def patterns_stability(X, y=None, n_clusters=None, folds=5, metric="ari", plot=True, darkstyle=False):
+    """Stability of the cluster assignments across folds (clustering/_clustering.py:471-605): half of the
+    rows are held out, a KMeansLeida model is fitted on every training fold of the other half (on the GPU),
+    each model labels the held-out rows, and the labelings are compared pairwise with ARI or AMI.
+    The random split and the k-means restarts consume numpy's global RNG in the reference's order, so
+    np.random.seed(s) reproduces the reference's result.  `plot` / `darkstyle` are accepted and ignored.
+    Returns the (folds, folds) score matrix."""
+    from sklearn.metrics import adjusted_mutual_info_score, adjusted_rand_score
+    from sklearn.model_selection import KFold, StratifiedKFold, train_test_split
+    if not isinstance(metric, str) or metric not in ["ari", "ami"]:
+        raise Exception("'metric' must be either 'ari' or 'ami'")
+    if not isinstance(X, np.ndarray):
+        raise TypeError("'X' must be a 2D array!")
+    if y is None and n_clusters is None:
+        raise Exception("You must specify either predicted labels in 'y' or a number of clusters ('n_clusters').")
+    if y is not None:
+        if not isinstance(y, np.ndarray):
+            raise TypeError("'y' must be an array!")
+        n_clusters = int(np.unique(y).size)
+        X_tr, X_ts, y_tr, _ = train_test_split(X, y, stratify=y, train_size=.5)           # :544
+        splits = StratifiedKFold(n_splits=folds).split(X_tr, y_tr)
+    else:
+        X_tr, X_ts = train_test_split(X, train_size=.5)                                    # :546
+        splits = KFold(n_splits=folds).split(X_tr)
+    test_engine = KMeansEngine(np.ascontiguousarray(X_ts, dtype=np.float32))
+    predictions = np.empty((X_ts.shape[0], folds))
+    for i, (tr_idx, _) in enumerate(splits):                                              # :551-562
+        km = KMeansLeida(k=n_clusters)
+        km.fit(np.ascontiguousarray(X_tr[tr_idx], dtype=np.float32))
+        predictions[:, i] = km.predict(test_engine)
+    score = adjusted_rand_score if metric == "ari" else adjusted_mutual_info_score
+    scores = np.empty((folds, folds))
+    for a in range(folds):                                                                # :566-578
+        for b in range(folds):
+            scores[a, b] = score(predictions[:, a], predictions[:, b])
+    return scores

@@ -159,10 +159,26 @@ def pipeline_case():
     np.savez_compressed(os.path.join(OUT, "pipeline_case.npz"), **out)
 
 
+def stability_case():
+    """patterns_stability (clustering/_clustering.py:471-605) on the pipeline case's eigenvectors; the global
+    RNG is seeded right before each call (it drives the train/test split and the k-means restarts)."""
+    import contextlib, io
+    g = np.load(os.path.join(OUT, "pipeline_case.npz"))
+    X = np.array(g["lei"], dtype=np.float32)
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        np.random.seed(5)
+        out["ari_y"] = ref.patterns_stability(X, y=g["labels_k3"], folds=4, metric="ari", plot=False)
+        np.random.seed(6)
+        out["ami_nc"] = ref.patterns_stability(X, n_clusters=4, folds=3, metric="ami", plot=False)
+    np.savez_compressed(os.path.join(OUT, "stability_case.npz"), **out)
+
+
 if __name__ == "__main__":
     signal_cases()
     kmeans_cases()
     metric_cases()
     pipeline_case()
+    stability_case()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

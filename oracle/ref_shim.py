@@ -66,6 +66,7 @@ def load_reference():
         get_eigenvectors=st.get_eigenvectors,
         KMeansLeida=cl.KMeansLeida,
         identify_states=cl.identify_states,
+        patterns_stability=cl.patterns_stability,
         fractional_occupancy=dm.fractional_occupancy,
         fractional_occupancy_group=dm.fractional_occupancy_group,
         dwell_times=dm.dwell_times,

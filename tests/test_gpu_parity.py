@@ -488,3 +488,36 @@ def test_results_folder_layout(P, tmp_path, monkeypatch):
     np.testing.assert_allclose(occ.iloc[:, 2:].values, m.occupancies(3).iloc[:, 2:].values.astype(float), atol=1e-15)
     with pytest.raises(Warning):
         P.Leida.from_arrays(ts, classes).fit_predict(TR=1.0, save_results=True, K_min=2, K_max=2, n_init=1)
+
+
+# ---- callers of predict / transform ---------------------------------------------------
+def test_patterns_stability_golden(P):
+    """Same global-RNG seed as the unmodified reference => same split, same restarts, same score matrix."""
+    g = np.load(os.path.join(GOLD, "pipeline_case.npz"))
+    s = np.load(os.path.join(GOLD, "stability_case.npz"))
+    X = np.array(g["lei"], dtype=np.float32)
+    np.random.seed(5)
+    got = P.clustering.patterns_stability(X, y=g["labels_k3"], folds=4, metric="ari", plot=False)
+    np.testing.assert_allclose(got, s["ari_y"], atol=1e-12)
+    np.random.seed(6)
+    got = P.clustering.patterns_stability(X, n_clusters=4, folds=3, metric="ami", plot=False)
+    np.testing.assert_allclose(got, s["ami_nc"], atol=1e-12)
+    with pytest.raises(Exception):
+        P.clustering.patterns_stability(X, metric="nmi")
+    with pytest.raises(Exception):
+        P.clustering.patterns_stability(X)
+
+
+def test_centroids_distances(P, O):
+    from pyleida import synthetic
+    ts, classes = synthetic.make_dataset(5, 10, 40, "states")
+    m = P.Leida.from_arrays(ts, classes).fit_predict(random_state=0, K_min=2, K_max=4, n_init=1)
+    d = m.centroids_distances(3)
+    assert list(d.columns) == ["subject_id", "condition", "centroid_1", "centroid_2", "centroid_3"]
+    X = m.eigenvectors.iloc[:, 2:].values.astype(np.float32)
+    ref = O.KMeansLeida(k=3)
+    ref.cluster_centers_, ref._is_fitted = m.load_model(3).cluster_centers_, True
+    np.testing.assert_allclose(d.iloc[:, 2:].values, ref.transform(X), atol=1e-13)
+    assert np.array_equal(np.argmin(d.iloc[:, 2:].values, axis=1), m.predictions["k_3"].values)
+    with pytest.raises(ValueError):
+        m.centroids_distances(9)
