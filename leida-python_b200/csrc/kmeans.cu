@@ -232,15 +232,16 @@ __global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
 // 1 - dot/(|x||c|) with clipping, first minimum wins.  (scipy's own build sums the dot product in two
 // SIMD lanes, so no particular fp64 summation order is "the" reference; any fp64 order agrees with it
 // to ~1e-16 and decides identically unless two distances coincide to that level.)
-constexpr int RECHECK_MAX_COLS_PER_LANE = 8;   // rows up to 256 columns stay in registers
-
+// CPL = columns per lane held in registers (rows up to 32*CPL columns); CPL = 0: rows stay in memory.
+template <int CPL>
 __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
+    constexpr int RECHECK_MAX_COLS_PER_LANE = CPL > 0 ? CPL : 1;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     long long count = p.worklist[0];
     if (count > p.worklist_cap) count = p.worklist_cap;
-    const bool in_regs = p.N <= 32 * RECHECK_MAX_COLS_PER_LANE;
+    constexpr bool in_regs = CPL > 0;
     for (long long e = warp; e < count; e += nwarps) {
         const int run = p.worklist[8 + 2 * e];
         const long long row = p.worklist[8 + 2 * e + 1];
@@ -500,8 +501,7 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
 // runs are staged in shared memory with coalesced loads, and four runs are in flight per warp.
 constexpr int DIST_ROWS = 32;
 constexpr int DIST_RUN_CHUNK = 256;
-constexpr int DIST_MAX_COLS_PER_LANE = 8;
-
+template <int CPL>
 __global__ void __launch_bounds__(256)
 k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long long M, int N, int XP, int n_runs,
              const int32_t* __restrict__ run_crow0, const float* __restrict__ cent,
@@ -511,7 +511,8 @@ k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long
     __shared__ int s_c0[DIST_RUN_CHUNK];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long row0 = (long long)blockIdx.x * DIST_ROWS;
-    const bool in_regs = N <= 32 * DIST_MAX_COLS_PER_LANE;
+    constexpr int DIST_MAX_COLS_PER_LANE = CPL > 0 ? CPL : 1;
+    constexpr bool in_regs = CPL > 0;
     for (int r0 = 0; r0 < n_runs; r0 += DIST_RUN_CHUNK) {
         const int nr = min(DIST_RUN_CHUNK, n_runs - r0);
         __syncthreads();
@@ -804,7 +805,12 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
     p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out;
-    k_recheck<<<sm_count() * 4, 128, 0, (cudaStream_t)stream>>>(p);
+    const int grid = sm_count() * (N > 256 ? 10 : 4);      // wide rows: more warps in flight hide the centroid loads
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 128) k_recheck<4><<<grid, 128, 0, st>>>(p);
+    else if (N <= 256) k_recheck<8><<<grid, 128, 0, st>>>(p);
+    else if (N <= 512) k_recheck<16><<<grid, 128, 0, st>>>(p);
+    else k_recheck<0><<<grid, 128, 0, st>>>(p);
     return check_launch("k_recheck");
 }
 
@@ -836,8 +842,10 @@ extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int6
     if (rc) return rc;
     k_zero_dist<<<(n_runs + 127) / 128, 128, 0, st>>>((long long*)state, n_runs);
     if (M > 0) {
-        k_distortion<<<(unsigned)((M + DIST_ROWS - 1) / DIST_ROWS), 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0,
-                                                                                  cent, cnorm, labels, (long long*)state);
+        const unsigned grid = (unsigned)((M + DIST_ROWS - 1) / DIST_ROWS);
+        if (N <= 128) k_distortion<4><<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state);
+        else if (N <= 256) k_distortion<8><<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state);
+        else k_distortion<0><<<grid, 256, 0, st>>>   /* wider rows: occupancy beats register residency (measured at N=400) */(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state);
     }
     return check_launch("k_distortion", M > 0 ? 2 : 1);
 }

@@ -513,9 +513,11 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     __shared__ int s_cin[LEIDA_KM_MAX_K + 1], s_cout[LEIDA_KM_MAX_K + 1], s_pin[LEIDA_KM_MAX_K], s_pout[LEIDA_KM_MAX_K];
     __shared__ int s_n;
     const int AP = XP + 8;
-    const long long row_base = (long long)blockIdx.x * APPLY_ROWS;
+    // blockIdx.y = row chunk, blockIdx.x = run slot: the CTAs that share a chunk have consecutive ids, are
+    // scheduled together and find the chunk's rows in L2 after the first of them has read them
+    const long long row_base = (long long)blockIdx.y * APPLY_ROWS;
     const int n_packed = plan[1];
-  for (int pr = blockIdx.y; pr < n_packed; pr += gridDim.y) {      // persistent over the packed runs
+  for (int pr = blockIdx.x; pr < n_packed; pr += gridDim.x) {      // persistent over the packed runs
     const int run = prun[pr];
     if (state[(long long)run * kStateWordsTc + LEIDA_KM_ST_ACTIVE] == 0) continue;
     const int K = run_k[run], crow0 = run_crow0[run];
@@ -714,7 +716,7 @@ extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x
                                      int64_t* acc, int64_t* state, leida_stream_t stream) {
     LEIDA_REQUIRE(X && plan && prun && run_k && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
     LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && n_runs_bound >= 1 && n_runs_bound <= 65535, "sizes");
-    dim3 grid((unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS), (unsigned)(n_runs_bound < 48 ? n_runs_bound : 48));
+    dim3 grid((unsigned)(n_runs_bound < 48 ? n_runs_bound : 48), (unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS));
     k_diff_apply<<<grid, APPLY_THREADS, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, plan, prun, run_k, run_crow0,
                                                                    labels_cur, labels_new, (long long*)acc,
                                                                    (long long*)state);

@@ -51,7 +51,7 @@ __global__ void k_scores_cluster_sums(const float* __restrict__ xs, long long XP
 }
 
 // silhouette sum per label column: one warp per row, the row in registers (fp64).
-constexpr int SCORE_MAX_COLS_PER_LANE = 8;
+constexpr int SCORE_MAX_COLS_PER_LANE = 16;
 __global__ void __launch_bounds__(256)
 k_scores_silhouette(const float* __restrict__ xs, long long XP, int N, long long n, const int32_t* __restrict__ labels,
                     long long label_pitch, const long long* __restrict__ sel, int n_cols,
