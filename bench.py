@@ -325,10 +325,10 @@ def native_arm(args):
     roofline = {"kernel": "k_tc_assign (tcgen05 bf16x3 distance GEMM + top-2 epilogue)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch that serves all 285 runs of this
-                # workload (ncu --set full, profiles/r01_k_tc_assign_ncu_full.txt capture C: 64.2 MB read =
-                # one pass over the bf16x2 rows, 95.3 MB written = the int32 labels); that launch's algorithmic
+                # workload (ncu --set full, profiles/r01_k_tc_assign_ncu_full.txt capture D: 64.3 MB read =
+                # one pass over the bf16x2 rows, 99.7 MB written = the int32 labels); that launch's algorithmic
                 # bytes on the SURVEY metric are 285 x 56.5 MB = 16.1 GB
-                "traffic": 159.5e6 if (world == 1 and wl["S"] == 100 and wl["N"] == 116) else None,
+                "traffic": 164.0e6 if (world == 1 and wl["S"] == 100 and wl["N"] == 116) else None,
                 "traffic_launch": "full pass, 285 active runs (captured once with ncu; per-launch traffic shrinks with the active-run count)",
                 "peak_source": peak_src, "launches": n_assign, "avg_launch_ms": assign_ms / max(n_assign, 1),
                 "share_of_step": assign_ms / ms,
