@@ -318,7 +318,7 @@ def native_arm(args):
     achieved = alg_bytes / (assign_ms * 1e-3) / 1e9 if assign_ms > 0 else 0.0
     # what the tensor-core kernel really does per launch: one read of the bf16 x 2 split rows for ALL
     # active runs, and 3 bf16 MMAs (X1*C1 + X1*C2 + X2*C1) per output
-    npk = (wl["N"] + 63) // 64 * 64
+    npk = int(nvl.lib.leida_kmeans_tc_pitch(wl["N"]))
     sum_k_passes = stats["sum_k_passes"]
     tensor_flops = 3 * 2.0 * M_local * npk * sum_k_passes * args.steps
     actual_bytes = n_assign * (2 * 2.0 * M_local * npk) + 4.0 * M_local * run_passes * args.steps

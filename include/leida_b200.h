@@ -162,26 +162,31 @@ int leida_kmeans_assign(const float* X, const double* xnorm, int64_t M, int N, i
 /* fp64 re-evaluation of the queued rows with the reference's arithmetic order (scipy cdist
  * 'cosine': sequential dot, dot/(|u||v|), clip, 1-cos; first minimum); empties the queue. */
 int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
-                         const int32_t* run_k, const int32_t* run_crow0,
+                         int n_runs, const int32_t* run_k, const int32_t* run_crow0,
                          const float* cent, const double* cnorm, int64_t* acc,
                          int32_t* labels, int64_t* state,
                          int32_t* worklist, int64_t worklist_cap, int32_t* labels_out, leida_stream_t stream);
 /* labels_out == NULL: the exact label replaces labels[run][row] and the row's contribution is moved
  * in acc (SIMT flow).  labels_out != NULL: the exact label is written to labels_out[run][row] only
- * (tensor-core flow; leida_kmeans_tc_apply does the moves). */
+ * (tensor-core flow; leida_kmeans_tc_apply does the moves).  In that flow a full queue is not an error:
+ * leida_kmeans_tc_assign marks every undecided pair with label -2, and when the queue overflowed the
+ * re-check also scans labels_out of the n_runs runs for marks that are not in the queue. */
 
 /* ---- tensor-core assignment flow (tcgen05 / TMEM / TMA) -------------------------------------
  * Same semantics as leida_kmeans_assign for ALL active runs in one launch:
  *   S = X * C'^T on the tensor cores with bf16 x 3 split operands (fp32-grade products), fused
  *   top-2 epilogue, fp64 re-check of every row inside the error bound.  Per pass:
- *     leida_kmeans_tc_assign  -> labels_new (label, or -2 = queued for the re-check)
+ *     leida_kmeans_tc_assign  -> labels_new (label, or -2 = undecided at this precision: queued for the re-check,
+ *                                or merely marked when the queue is full)
  *     leida_kmeans_recheck(labels_out = labels_new)
  *     leida_kmeans_tc_apply   -> changed counts, fixed-point moves in acc, labels_cur := labels_new
  *     [all-reduce acc/state]  leida_kmeans_update
  *     leida_kmeans_tc_plan    -> packs the still-active runs' unit-normalised centroids for the next pass
  * X1/X2: bf16 (M, tc_pitch) split of X (leida_kmeans_tc_split_rows, once per data set).
- * C1/C2: bf16 (c_rows, tc_pitch) packed centroid operands; c_rows >= 128 * (number of tiles), a
- *        bound is 2*sum(K) + 128.  plan (2), tile_first/tile_count (c_rows/128), prun/pcol/run_pcol
+ * C1/C2: bf16 (c_rows, tc_pitch) packed centroid operands; every run owns a slot of 4/8/12/16/20/24/32/
+ *        40/48/64 columns (its K unit centroids + padding columns that score -1e30 through a constant
+ *        bias feature), a 128-column tile holds slots of one width; c_rows >= 128 * (number of tiles),
+ *        a bound is 2*sum(K) + 128*12.  plan (2), tile_first/tile_count (c_rows/128), prun/pcol/run_pcol
  *        (n_runs): int32 device arrays owned by the caller, written by leida_kmeans_tc_plan. */
 int64_t leida_kmeans_tc_pitch(int N);
 int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch, void* X1, void* X2,

@@ -54,6 +54,12 @@ __device__ __forceinline__ double cosine_distance(double dot, double na, double 
     return 1.0 - c;
 }
 
+// Width (in packed centroid columns) of the slot / TMEM read that holds a run of K clusters.
+__host__ __device__ __forceinline__ int tc_read_width(int K) {
+    return K <= 4 ? 4 : K <= 8 ? 8 : K <= 12 ? 12 : K <= 16 ? 16 : K <= 20 ? 20 : K <= 24 ? 24 : K <= 32 ? 32 : K <= 40 ? 40
+         : K <= 48 ? 48 : 64;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -51,6 +51,7 @@ struct AssignParams {
     long long worklist_cap;
     float tau0;
     int32_t* labels_out;  // recheck only: when set, write the exact label here and leave the move to the caller
+    int n_runs;           // recheck only: runs to scan when the queue overflowed
 };
 
 // Move one row's fixed-point contribution between clusters.  Called by `nthreads` cooperating
@@ -239,12 +240,10 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    long long count = p.worklist[0];
-    if (count > p.worklist_cap) count = p.worklist_cap;
+    const long long queued = p.worklist[0];
+    const long long count = queued > p.worklist_cap ? p.worklist_cap : queued;
     constexpr bool in_regs = CPL > 0;
-    for (long long e = warp; e < count; e += nwarps) {
-        const int run = p.worklist[8 + 2 * e];
-        const long long row = p.worklist[8 + 2 * e + 1];
+    auto resolve = [&](int run, long long row) {
         const int K = p.run_k[run];
         const int crow0 = p.run_crow0[run];
         const float* xr = p.X + row * p.XP;
@@ -300,7 +299,7 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
                 p.labels_out[(long long)run * p.M + row] = bk;
                 atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
             }
-            continue;
+            return;
         }
         int32_t* lab = p.labels + (long long)run * p.M;
         const int old_l = lab[row];
@@ -313,6 +312,26 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
             move_row(p, row, crow0, old_l, bk, lane, 32);
         }
         if (lane == 0) atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
+    };
+    for (long long e = warp; e < count; e += nwarps) resolve(p.worklist[8 + 2 * e], p.worklist[8 + 2 * e + 1]);
+    // Queue overflow (tensor-core flow only; its fast pass stores -2 for every undecided pair whether or
+    // not the pair still fitted in the queue): find the unlisted pairs by scanning the labels of the
+    // active runs.  A pair another warp is resolving from the queue right now may be resolved twice --
+    // same inputs, same label.
+    if (p.labels_out && queued > p.worklist_cap) {
+        const long long blocks = (p.M + 31) / 32;
+        for (long long b = warp; b < (long long)p.n_runs * blocks; b += nwarps) {
+            const int run = (int)(b / blocks);
+            if (p.state[(long long)run * kStateWords + LEIDA_KM_ST_ACTIVE] == 0) continue;
+            const long long row0 = (b - run * blocks) * 32;
+            const bool mine = row0 + lane < p.M && p.labels_out[(long long)run * p.M + row0 + lane] == -2;
+            unsigned todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {
+                const int bit = __ffs(todo) - 1;
+                todo &= todo - 1;
+                resolve(run, row0 + bit);
+            }
+        }
     }
     // the last CTA to finish clears the list header for the next assign launch
     __syncthreads();
@@ -479,10 +498,13 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
     // Written for every packed run (also one that just stopped), so the packed matrix never holds
     // stale rows of another run after a re-plan.
     if (pc >= 0) {
-        for (int i = threadIdx.x; i < K * NPK; i += blockDim.x) {
+        const int W = tc_read_width(K);                // the run's slot: K centroids + padding columns that score -1e30
+        for (int i = threadIdx.x; i < W * NPK; i += blockDim.x) {
             const int k = i / NPK, j = i - k * NPK;
             float v = 0.f;
-            if (j < N) {
+            if (k >= K) {
+                v = j == N ? -1e30f : 0.f;
+            } else if (j < N) {
                 const double cn = cnorm[crow0 + k];
                 const float inv = cn > 0.0 ? (float)(1.0 / cn) : 0.f;
                 v = cent[(long long)(crow0 + k) * XP + j] * inv;
@@ -794,7 +816,7 @@ extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t 
 }
 
 extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
-                                    const int32_t* run_k, const int32_t* run_crow0, const float* cent,
+                                    int n_runs, const int32_t* run_k, const int32_t* run_crow0, const float* cent,
                                     const double* cnorm, int64_t* acc, int32_t* labels, int64_t* state,
                                     int32_t* worklist, int64_t worklist_cap, int32_t* labels_out,
                                     leida_stream_t stream) {
@@ -804,7 +826,7 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
     p.X = X; p.xnorm = xnorm; p.M = M; p.N = N; p.XP = (int)x_pitch;
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
-    p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out;
+    p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out; p.n_runs = n_runs;
     const int grid = sm_count() * (N > 256 ? 10 : 4);      // wide rows: more warps in flight hide the centroid loads
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 128) k_recheck<4><<<grid, 128, 0, st>>>(p);
@@ -825,7 +847,7 @@ extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32
     LEIDA_REQUIRE(n_iter >= 0, "n_iter >= 0");
     LEIDA_CUDA_TRY(cudaMemsetAsync(n_active_out, 0, sizeof(int32_t), st));
     LEIDA_REQUIRE((run_pcol == nullptr) == (C1 == nullptr) && (C1 == nullptr) == (C2 == nullptr), "run_pcol, C1, C2 together");
-    const int NPK = (int)(((int64_t)N + 63) / 64 * 64);
+    const int NPK = (int)(((int64_t)N + 1 + 63) / 64 * 64);     // = leida_kmeans_tc_pitch(N)
     k_update<<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, (const long long*)acc_reduced,
                                      (const long long*)state_reduced, cent, cnorm, (long long*)state, n_iter, n_active_out,
                                      run_pcol, (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK, mailbox);

@@ -8,8 +8,8 @@
 // trusts the argmax only when the margin exceeds a rigorous error bound and queues the other rows for
 // the fp64 re-check (leida_kmeans_recheck), so labels are still the fp64 argmin of the reference.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..5 epilogue
-// (one TMEM lane quarter each).  Persistent over row tiles of 128 rows; for every row tile all column
+// CTA = 18 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..17 epilogue
+// (four per TMEM lane quarter).  Persistent over row tiles of 128 rows; for every row tile all column
 // tiles (128 packed centroid columns) are visited, K streamed in 64-element (128-byte, swizzled) blocks.
 #include "common.cuh"
 #include <cuda.h>
@@ -24,7 +24,8 @@ constexpr int BN = 128;          // packed centroid columns per tile (UMMA N)
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int ST = 3;            // smem pipeline stages
 constexpr int STAGE_BYTES = 4 * BM * BK * 2;          // X1, X2, C1, C2 blocks: 64 KB
-constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter
+constexpr int EPI_SPLIT = 4;                          // epilogue warps per TMEM lane quarter
+constexpr int EPI_WARPS = 4 * EPI_SPLIT;
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 256;                        // two fp32 accumulators of BN columns
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
@@ -108,39 +109,36 @@ template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t t, uint32_t* r)
 template <> __device__ __forceinline__ void tmem_ld<64>(uint32_t t, uint32_t* r) { tmem_ld_x64(t, r); }
 template <> __device__ __forceinline__ void tmem_ld<0>(uint32_t, uint32_t*) {}
 
-// Width (power-of-two pieces W1 + W2) of the TMEM read that covers a run of K columns.
-__host__ __device__ __forceinline__ int read_width(int K) {
-    return K <= 4 ? 4 : K <= 8 ? 8 : K <= 12 ? 12 : K <= 16 ? 16 : K <= 20 ? 20 : K <= 24 ? 24 : K <= 32 ? 32 : K <= 40 ? 40
-         : K <= 48 ? 48 : 64;
-}
+__host__ __device__ __forceinline__ int read_width(int K) { return tc_read_width(K); }
 
-// Top-2 of a run's K scores held in registers (read from TMEM).  The cluster index is packed into
-// the 6 low mantissa bits of each score (a 2^-17 relative perturbation, covered by the error bound),
-// which makes every key unique: best = max tree, second = max tree over the keys != best.  All trees
-// are fully unrolled over the read width, so the work is instruction-level parallel, not a chain.
+// Top-2 of a run's scores held in registers (read from TMEM).  The run owns a slot of W columns: its
+// K centroids followed by W-K padding columns that score -1e30 by construction (bias feature, see
+// k_split_rows / pack), so no per-column masking is needed.  The cluster index is packed into the 6 low
+// mantissa bits of each score (a 2^-17 relative perturbation, covered by the error bound), which makes
+// every key unique.  (best, second) are computed together in one tree of pair merges:
+//   (m1,s1) + (m2,s2) -> (max(m1,m2), max(min(m1,m2), s1, s2))        2.5 W min/max operations in all.
 template <int W>
-__device__ __forceinline__ void top2_regs(const uint32_t* r, int K, float& best, float& second, int& bk) {
-    float key[W];
+__device__ __forceinline__ void top2_regs(const uint32_t* r, float& best, float& second, int& bk) {
+    constexpr int P = W / 2;
+    float m[P], s2[P];
 #pragma unroll
-    for (int k = 0; k < W; ++k)
-        key[k] = k < K ? __uint_as_float((r[k] & 0xFFFFFFC0u) | (uint32_t)k) : -INFINITY;
-    float m[W];
+    for (int k = 0; k < P; ++k) {
+        const float a = __uint_as_float((r[2 * k] & 0xFFFFFFC0u) | (uint32_t)(2 * k));
+        const float b = __uint_as_float((r[2 * k + 1] & 0xFFFFFFC0u) | (uint32_t)(2 * k + 1));
+        m[k] = fmaxf(a, b);
+        s2[k] = fminf(a, b);
+    }
 #pragma unroll
-    for (int k = 0; k < W; ++k) m[k] = key[k];
+    for (int o = 1; o < P; o <<= 1)
 #pragma unroll
-    for (int o = 1; o < W; o <<= 1)
-#pragma unroll
-        for (int k = 0; k + o < W; k += 2 * o) m[k] = fmaxf(m[k], m[k + o]);
-    const float b = m[0];
-#pragma unroll
-    for (int k = 0; k < W; ++k) m[k] = (key[k] == b) ? -INFINITY : key[k];
-#pragma unroll
-    for (int o = 1; o < W; o <<= 1)
-#pragma unroll
-        for (int k = 0; k + o < W; k += 2 * o) m[k] = fmaxf(m[k], m[k + o]);
-    bk = (int)(__float_as_uint(b) & 63u);
-    best = __uint_as_float(__float_as_uint(b) & 0xFFFFFFC0u);
-    second = __uint_as_float(__float_as_uint(m[0]) & 0xFFFFFFC0u);
+        for (int k = 0; k + o < P; k += 2 * o) {
+            const float lo = fminf(m[k], m[k + o]);
+            m[k] = fmaxf(m[k], m[k + o]);
+            s2[k] = fmaxf(lo, fmaxf(s2[k], s2[k + o]));
+        }
+    bk = (int)(__float_as_uint(m[0]) & 63u);
+    best = __uint_as_float(__float_as_uint(m[0]) & 0xFFFFFFC0u);
+    second = __uint_as_float(__float_as_uint(s2[0]) & 0xFFFFFFC0u);
 }
 
 // The registers written by tcgen05.ld become valid only after tcgen05.wait::ld; this empty asm makes
@@ -150,11 +148,6 @@ __device__ __forceinline__ void reg_fence(uint32_t* r) {
 #pragma unroll
     for (int k = 0; k < W; ++k) asm volatile("" : "+r"(r[k]));
 }
-
-// Rare path, kept out of line: queue the (run,row) pair for the fp64 re-check, or resolve it here
-// (serially, exactly) when the queue is full.  Returns the label to store (-2 = queued).
-struct TcParams;
-__device__ __noinline__ int defer_row(const TcParams& p, int run, long long row, int K);
 
 // Packing plan written by k_plan (device), read by the assign kernel.
 //   plan[0] = number of column tiles, plan[1] = number of packed (active) runs
@@ -175,91 +168,72 @@ struct TcParams {
     int32_t* labels_new;
     int32_t* worklist;
     long long worklist_cap;
-    // for the (slow, exact) inline resolution when the work list is full
-    const float* X;
-    int XP;
-    int N;
-    const float* cent;
-    const double* cnorm;
-    const int32_t* run_crow0;
-    long long* state;
 };
 
-__device__ __noinline__ int defer_row(const TcParams& p, int run, long long row, int K) {
-    const int slot = atomicAdd(p.worklist, 1);
-    if (slot < p.worklist_cap) {
-        p.worklist[8 + 2 * (long long)slot] = run;
-        p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
-        return -2;
+// Columns one epilogue step reads from TMEM for a tile whose slots are W wide: a whole number of slots,
+// a divisor-friendly size so that no step reaches past the tile's BN columns, and (for the narrow
+// slots that dominate the sweep) as wide as one tcgen05.ld allows, because the epilogue is bound by the
+// TMEM load round trip, not by the arithmetic.
+__host__ __device__ constexpr int chunk_cols(int W) { return W == 4 || W == 8 || W == 16 ? 32 : W == 12 ? 24 : W; }
+
+template <int CH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t t, uint32_t* r) {
+    if constexpr (CH == 64) tmem_ld_x64(t, r);
+    else {
+        constexpr int A = CH >= 32 ? 32 : 16;      // CH in {20, 24, 32, 40, 48}
+        tmem_ld<A>(t, r);
+        tmem_ld<CH - A>(t + A, r + A);
     }
-    const int crow0 = p.run_crow0[run];
-    const float* xr = p.X + row * p.XP;
-    const double xnd = p.xnorm[row];
-    double bd = INFINITY;
-    int out = 0;
-    for (int k = 0; k < K; ++k) {
-        const double d = cosine_distance(dot_seq(xr, p.cent + (long long)(crow0 + k) * p.XP, p.N), xnd, p.cnorm[crow0 + k]);
-        if (d < bd) { bd = d; out = k; }
-    }
-    atomicAdd(reinterpret_cast<unsigned long long*>(p.state + (long long)run * kStateWordsTc + LEIDA_KM_ST_RECHECKED), 1ull);
-    return out;
 }
 
-// Epilogue of one column tile for one warp: its runs are i = half, half+2, ... of the tile's run
-// list (at most 32 per warp, so one coalesced metadata load + shuffles).  Software pipelined: the
-// TMEM columns of the next run are in flight while the current run's top-2 is computed.
-template <int W1, int W2>
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int first, int cnt, int half, int lane,
+// Epilogue of one column tile for one warp.  All slots of a tile have the same width W and sit at
+// columns 0, W, 2W, ... (k_plan), so the warp reads the tile in chunks of CH columns = CH/W runs per
+// tcgen05.ld and evaluates the runs from registers; the EPI_SPLIT warps of a lane quarter take the chunks
+// round-robin.  (Software pipelining the loads was measured and bought nothing: with this many warps the
+// scheduler already overlaps one warp's TMEM round trip with another's arithmetic.)
+template <int W>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int first, int cnt, int sub, int lane,
                                               bool valid, float thr, int32_t* lab, long long row) {
-    constexpr int W = W1 + W2;
-    const int n_mine = (cnt - half + 1) >> 1;
-    if (n_mine <= 0) return;
-    const int mi = half + 2 * lane;
-    const int mine = mi < cnt ? first + mi : first;
-    const int m_run = p.prun[mine], m_col = p.pcol[mine];
-    uint32_t ra[W], rb[W <= 24 ? W : 1];
-    auto issue = [&](int b, uint32_t* r) {
-        const int c0 = __shfl_sync(0xffffffffu, m_col, b) & 0xff;
-        tmem_ld<W1>(taddr + c0, r);
-        tmem_ld<W2>(taddr + c0 + W1, r + W1);
-    };
-    auto finish = [&](int b, uint32_t* r) {
-        reg_fence<W>(r);
-        const int run = __shfl_sync(0xffffffffu, m_run, b);
-        const int K = __shfl_sync(0xffffffffu, m_col, b) >> 8;
-        float best, second;
-        int bk;
-        top2_regs<W>(r, K, best, second, bk);
-        if (valid) {
-            int out = bk;
-            if (!((best - second) > thr)) out = defer_row(p, run, row, K);
-            lab[(long long)run * p.M] = out;
-        }
-    };
-    if constexpr (W <= 24) {
-        issue(0, ra);
-        for (int b = 0; b < n_mine; b += 2) {
-            tmem_ld_wait();
-            if (b + 1 < n_mine) issue(b + 1, rb);
-            finish(b, ra);
-            if (b + 1 < n_mine) {
-                tmem_ld_wait();
-                if (b + 2 < n_mine) issue(b + 2, ra);
-                finish(b + 1, rb);
+    constexpr int CH = chunk_cols(W), RPC = CH / W;
+    const int n_chunks = (cnt + RPC - 1) / RPC;
+    if (sub >= n_chunks) return;
+    const int m_run = p.prun[first + (lane < cnt ? lane : 0)];     // a tile holds at most 32 runs
+    uint32_t r[CH];
+    for (int c = sub; c < n_chunks; c += EPI_SPLIT) {
+        tmem_ld_chunk<CH>(taddr + c * CH, r);
+        tmem_ld_wait();
+        reg_fence<CH>(r);
+#pragma unroll
+        for (int j = 0; j < RPC; ++j) {
+            const int i = c * RPC + j;
+            if (i < cnt) {                                         // warp-uniform
+                const int run = __shfl_sync(0xffffffffu, m_run, i);
+                float best, second;
+                int bk;
+                top2_regs<W>(r + j * W, best, second, bk);
+                if (valid) {
+                    int out = bk;
+                    if (!((best - second) > thr)) {
+                        // undecided at this precision: mark the pair and queue it for the fp64 re-check.  A full
+                        // queue is fine -- the re-check finds unlisted marks by scanning (k_recheck).
+                        out = -2;
+                        const int slot = atomicAdd(p.worklist, 1);
+                        if (slot < p.worklist_cap) {
+                            p.worklist[8 + 2 * (long long)slot] = run;
+                            p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
+                        }
+                    }
+                    lab[(long long)run * p.M] = out;
+                }
             }
-        }
-    } else {                                  // wide runs: one register set (few runs per tile anyway)
-        for (int b = 0; b < n_mine; ++b) {
-            issue(b, ra);
-            tmem_ld_wait();
-            finish(b, ra);
         }
     }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
-            const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
+            const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2,
+            const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* stages = base;                                         // ST * 64 KB
@@ -334,10 +308,9 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
                 }
         }
     } else if (n_ct > 0) {
-        // Epilogue: EPI_WARPS warps, two per TMEM lane quarter; the two warps of a quarter take the
-        // even / odd runs of every column tile.
+        // Epilogue: EPI_WARPS warps, EPI_SPLIT per TMEM lane quarter, which share every column tile's chunks.
         const int q = warp & 3;                       // TMEM lane quarter this warp may touch
-        const int half = (warp - 2) >> 2;             // 0 or 1
+        const int sub = (warp - 2) >> 2;              // which of the quarter's EPI_SPLIT warps
         const int r_in_tile = q * 32 + lane;
         int acc = 0;
         uint32_t aphase = 0;
@@ -348,21 +321,21 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
             int32_t* lab = p.labels_new + row;
             for (int ct = 0; ct < n_ct; ++ct) {
                 const int tf = p.tile_first[ct], cnt = p.tile_count[ct];
-                const int first = tf & 0xffff, wt = tf >> 16;      // wt = read width of the tile's widest run
+                const int first = tf & 0xffff, wt = tf >> 16;      // wt = slot width of the tile's runs
                 mbar_wait(&tfull[acc], aphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
                 switch (wt) {
-                    case 4: epilogue_tile<4, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 8: epilogue_tile<8, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 12: epilogue_tile<8, 4>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 16: epilogue_tile<16, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 20: epilogue_tile<16, 4>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 24: epilogue_tile<16, 8>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 32: epilogue_tile<32, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 40: epilogue_tile<32, 8>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    case 48: epilogue_tile<32, 16>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
-                    default: epilogue_tile<64, 0>(p, taddr, first, cnt, half, lane, valid, thr, lab, row); break;
+                    case 4: epilogue_tile<4>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 8: epilogue_tile<8>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 12: epilogue_tile<12>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 16: epilogue_tile<16>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 20: epilogue_tile<20>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 24: epilogue_tile<24>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 32: epilogue_tile<32>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 40: epilogue_tile<40>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 48: epilogue_tile<48>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    default: epilogue_tile<64>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);            // accumulator may be overwritten by the next tile
@@ -392,7 +365,9 @@ __global__ void k_split_rows(const float* __restrict__ X, long long M, int N, lo
     if (i >= M * NPK) return;
     const long long r = i / NPK;
     const int j = (int)(i - r * NPK);
-    const float v = j < N ? X[r * XP + j] : 0.f;
+    // column N is the constant bias feature (1 in the hi part): real centroids carry 0 there, the padding
+    // columns of a run's slot carry -1e30, so a padding column always scores -1e30
+    const float v = j < N ? X[r * XP + j] : (j == N ? 1.f : 0.f);
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
     X1[i] = hi;
@@ -414,15 +389,19 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
         s_k[r] = state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] != 0 ? (short)run_k[r] : (short)0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        int tile = 0, col = 0, np = 0;
+        int tile = 0, col = 0, np = 0, cur_w = 0;
         for (int r = 0; r < n_runs; ++r) {
             const int K = s_k[r];
             int pc = -1;
             if (K > 0) {
-                if (col + read_width(K) > BN) { ++tile; col = 0; }   // the TMEM read of the run must stay inside the tile
+                // a run owns a slot of read_width(K) columns; a tile holds slots of ONE width (runs arrive in
+                // ascending K, so a width change just closes the current tile)
+                const int w = read_width(K);
+                if (col > 0 && (col + w > BN || w != cur_w)) { ++tile; col = 0; }
+                cur_w = w;
                 pc = tile * BN + col;
-                s_tw[tile] = (short)read_width(K);     // runs arrive in ascending K: the last one is the widest
-                col += K;
+                s_tw[tile] = (short)w;
+                col += w;
                 ++np;
             }
             s_pc[r] = pc;
@@ -476,10 +455,13 @@ __global__ void k_pack_centroids(const int32_t* __restrict__ run_k, const int32_
     const int pc = run_pcol[run];
     if (pc < 0) return;
     const int K = run_k[run], crow0 = run_crow0[run];
-    for (int i = threadIdx.x; i < K * NPK; i += blockDim.x) {
+    const int W = read_width(K);
+    for (int i = threadIdx.x; i < W * NPK; i += blockDim.x) {
         const int k = i / NPK, j = i - k * NPK;
         float v = 0.f;
-        if (j < N) {
+        if (k >= K) {
+            v = j == N ? -1e30f : 0.f;                  // padding column of the slot: scores -1e30 for every row
+        } else if (j < N) {
             const double cn = cnorm[crow0 + k];
             const float inv = cn > 0.0 ? (float)(1.0 / cn) : 0.f;
             v = cent[(long long)(crow0 + k) * XP + j] * inv;
@@ -634,7 +616,8 @@ static int make_map(CUtensorMap* map, const void* ptr, long long rows, int NPK) 
 
 using namespace leida;
 
-extern "C" int64_t leida_kmeans_tc_pitch(int N) { return ((int64_t)N + BK - 1) / BK * BK; }
+// columns of the bf16 operands: N features + 1 constant "bias" feature, rounded up to whole k-blocks
+extern "C" int64_t leida_kmeans_tc_pitch(int N) { return ((int64_t)N + 1 + BK - 1) / BK * BK; }
 
 extern "C" int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch, void* X1, void* X2,
                                           leida_stream_t stream) {
@@ -696,8 +679,6 @@ extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const floa
     const float acc_term = 2.0f * (3.0f * (float)(NPK / 16) * 5.0f) * 1.1921e-7f;
     p.tau = 2.5f * (3.0f * 3.8147e-6f + 2.4e-7f + 7.63e-6f + acc_term);
     p.labels_new = labels_new; p.worklist = worklist; p.worklist_cap = worklist_cap;
-    p.X = X; p.XP = (int)x_pitch; p.N = N; p.cent = cent; p.cnorm = cnorm; p.run_crow0 = run_crow0;
-    p.state = (long long*)state;
     const size_t smem = 1024 + (size_t)ST * STAGE_BYTES + 32 * sizeof(uint64_t);
     static bool attr_set = false;      // once per process; keeps the call legal inside stream capture
     if (!attr_set) {

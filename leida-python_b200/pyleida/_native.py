@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libleida_b200.so")
+LIB_PATH = os.environ.get("LEIDA_B200_LIB") or os.path.join(_HERE, "_lib", "libleida_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -44,7 +44,7 @@ SIGNATURES = {
     "leida_kmeans_init": (c_int, [_P, c_int64, _P, c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P, c_int64, _P, _P]),
     "leida_kmeans_assign": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                     c_int64, _P]),
-    "leida_kmeans_recheck": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P]),
+    "leida_kmeans_recheck": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P]),
     "leida_kmeans_tc_pitch": (c_int64, [c_int]),
     "leida_kmeans_tc_split_rows": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P]),
     "leida_kmeans_tc_plan": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),

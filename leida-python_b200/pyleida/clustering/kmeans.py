@@ -135,6 +135,7 @@ class KMeansEngine:
         state = red_local[n_acc:].view(R, nv.STATE_WORDS)
         labels = torch.empty((R, self.M), dtype=torch.int32, device=dev)
         cap = int(min(max(R * self.M // 8, 1 << 16), 1 << 24))    # (run,row) pairs queued for the fp64 re-check per pass
+        cap = int(os.environ.get("LEIDA_KMEANS_WORKLIST_CAP", cap))   # tests shrink it to exercise the overflow path
         worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
         worklist[:8].zero_()
         n_active = torch.zeros(8, dtype=torch.int32, device=dev)
@@ -168,7 +169,9 @@ class KMeansEngine:
         tc = assign == "tc"
         if tc:
             x1, x2, npk = self._tc_operands()
-            c_rows = (2 * CR + 128 + 127) // 128 * 128
+            # packed columns: every run owns a slot of read_width(K) <= 2K columns; tiles hold one slot width each,
+            # so up to one partly filled tile per width class
+            c_rows = (2 * CR + 128 * 12 + 127) // 128 * 128
             c1 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
             c2 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
             labels_new = torch.empty((R, self.M), dtype=torch.int32, device=dev)
@@ -204,7 +207,7 @@ class KMeansEngine:
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
                         nv.ptr(worklist), cap, stq)
-                nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP,
+                nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
                         nv.ptr(worklist), cap, None, stq)
@@ -213,7 +216,7 @@ class KMeansEngine:
             stq = nv.stream()
             if tc:
                 timed("recheck", lambda: nv.call(
-                    "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, nv.ptr(run_k),
+                    "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
                     nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
                     nv.ptr(worklist), cap, nv.ptr(labels_new), stq))
                 timed("apply", lambda: nv.call(

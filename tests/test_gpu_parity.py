@@ -349,6 +349,25 @@ def test_tensor_core_and_cuda_core_assignment_agree(P):
         assert a.rechecked_total < 0.05 * a.total_passes() * M      # the fp64 re-check stays a rare path
 
 
+def test_recheck_queue_overflow_changes_nothing(P, monkeypatch):
+    """A re-check queue far too small for the undecided pairs (iid data, 64 slots) must give the same
+    labels, pass counts and inertia: the fast pass marks the pairs, the re-check scans for the marks."""
+    rng = np.random.default_rng(5)
+    M, N = 20_000, 90
+    X = rng.standard_normal((M, N)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    eng = P.clustering.KMeansEngine(X)
+    runs = [(k, rng.choice(M, k, replace=False)) for k in (2, 5, 12, 20) for _ in range(2)]
+    a = eng.run(runs, n_iter=20, assign="tc")
+    monkeypatch.setenv("LEIDA_KMEANS_WORKLIST_CAP", "64")
+    b = eng.run(runs, n_iter=20, assign="tc")
+    assert a.rechecked_total > 64                  # the small queue did overflow
+    for i in range(len(runs)):
+        assert a.passes(i) == b.passes(i), i
+        assert a.inertia(i) == b.inertia(i), i
+        assert bool((a.labels_device(i) == b.labels_device(i)).all()), i
+
+
 def test_wide_rows_rank2_and_dense_eigenvectors(P, O):
     """N = 1000 ROIs (BASELINE config 4 shape, few volumes): closed form and general solver."""
     from pyleida import synthetic
