@@ -53,6 +53,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    """Dense bf16 TFLOP/s: the burst figure, because k_tc_assign launches are short and isolated."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)"
+    return 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -325,16 +335,18 @@ def native_arm(args):
     roofline = {"kernel": "k_tc_assign (tcgen05 bf16x3 distance GEMM + top-2 epilogue)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch that serves all 285 runs of this
-                # workload (ncu --set full, profiles/r01_k_tc_assign_ncu_full.txt capture D: 64.3 MB read =
-                # one pass over the bf16x2 rows, 99.7 MB written = the int32 labels); that launch's algorithmic
+                # workload (ncu --set full, profiles/r01_k_tc_assign_ncu_full.txt capture E: 64.6 MB read =
+                # one pass over the bf16x2 rows, 89.2 MB written = the int32 labels); that launch's algorithmic
                 # bytes on the SURVEY metric are 285 x 56.5 MB = 16.1 GB
-                "traffic": 164.0e6 if (world == 1 and wl["S"] == 100 and wl["N"] == 116) else None,
+                "traffic": 153.8e6 if (world == 1 and wl["S"] == 100 and wl["N"] == 116) else None,
                 "traffic_launch": "full pass, 285 active runs (captured once with ncu; per-launch traffic shrinks with the active-run count)",
                 "peak_source": peak_src, "launches": n_assign, "avg_launch_ms": assign_ms / max(n_assign, 1),
                 "share_of_step": assign_ms / ms,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_assign, 1),
                 "actual_bytes_per_launch_model": actual_bytes / max(n_assign, 1),
                 "tensor_tflops_bf16": tensor_flops / (assign_ms * 1e-3) / 1e12 if assign_ms > 0 else 0.0,
+                "tensor_peak_tflops_bf16": tensor_peak()[0], "tensor_peak_source": tensor_peak()[1],
+                "tensor_frac": (tensor_flops / (assign_ms * 1e-3) / 1e12 / tensor_peak()[0]) if assign_ms > 0 else 0.0,
                 "other_kernels_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items() if k != "assign"},
                 "note": "algorithmic bytes = (4*M*N + 8*M) per run per Lloyd pass (SURVEY 8d). One launch serves every "
                         "active run of the pass from ONE read of the rows (a tensor-core contraction over all runs' "
