@@ -235,6 +235,7 @@ def native_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keeps NCCL's version banner out of the JSON on stdout
         dist.init_process_group("nccl", device_id=dev)
     import pyleida
     from pyleida import _native as nvl

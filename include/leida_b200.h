@@ -183,10 +183,11 @@ int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, 
  *     [all-reduce acc/state]  leida_kmeans_update
  *     leida_kmeans_tc_plan    -> packs the still-active runs' unit-normalised centroids for the next pass
  * X1/X2: bf16 (M, tc_pitch) split of X (leida_kmeans_tc_split_rows, once per data set).
- * C1/C2: bf16 (c_rows, tc_pitch) packed centroid operands; every run owns a slot of 4/8/12/16/20/24/32/
- *        40/48/64 columns (its K unit centroids + padding columns that score -1e30 through a constant
- *        bias feature), a 128-column tile holds slots of one width; c_rows >= 128 * (number of tiles),
- *        a bound is 2*sum(K) + 128*12.  plan (2), tile_first/tile_count (c_rows/128), prun/pcol/run_pcol
+ * C1/C2: bf16 (c_rows, tc_pitch) packed centroid operands; every run owns a slot of 4..64 columns (a
+ *        multiple of 4: its K unit centroids + padding columns that score -1e30 through a constant bias
+ *        feature), a 128-column tile holds slots of one width; the plan may give a run a wider slot than
+ *        its K needs so that part-filled tiles of different widths merge.  c_rows >= 128 * (number of
+ *        tiles), a bound is 2*sum(K) + 128*12.  run_pcol[r] = first packed column | slot width << 24, or -1.  plan (2), tile_first/tile_count (c_rows/128), prun/pcol/run_pcol
  *        (n_runs): int32 device arrays owned by the caller, written by leida_kmeans_tc_plan. */
 int64_t leida_kmeans_tc_pitch(int N);
 int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch, void* X1, void* X2,

@@ -451,7 +451,7 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
         if (go) atomicAdd(n_active, 1);
     }
     __syncthreads();
-    const int pc = run_pcol ? run_pcol[run] : -1;
+    const int pv = run_pcol ? run_pcol[run] : -1;      // packed column | slot width << 24 (k_plan)
     if (s_go) {
         for (int i = threadIdx.x; i < K * XP; i += blockDim.x) {
             const int k = i / XP, j = i - k * XP;
@@ -497,8 +497,8 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
     // tensor-core operands of this run at its packed position: unit-normalised centroids, bf16 hi/lo.
     // Written for every packed run (also one that just stopped), so the packed matrix never holds
     // stale rows of another run after a re-plan.
-    if (pc >= 0) {
-        const int W = tc_read_width(K);                // the run's slot: K centroids + padding columns that score -1e30
+    if (pv >= 0) {
+        const int W = pv >> 24, pc = pv & 0xFFFFFF;    // the run's slot: K centroids + padding columns that score -1e30
         for (int i = threadIdx.x; i < W * NPK; i += blockDim.x) {
             const int k = i / NPK, j = i - k * NPK;
             float v = 0.f;

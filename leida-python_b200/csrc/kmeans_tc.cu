@@ -374,74 +374,84 @@ __global__ void k_split_rows(const float* __restrict__ X, long long M, int N, lo
     X2[i] = lo;
 }
 
-// Packing plan: active runs, in run order, placed side by side so that no run straddles a BN-column
-// tile.  One CTA: the run table is staged in shared memory with coalesced loads, one thread does the
-// (inherently sequential, ~10 cycles per run) placement, all threads write the result back.
+// Packing plan: every active run gets a slot of W columns (W >= read_width(K)) inside a BN-column tile
+// whose slots all have the same width.  Normally W = read_width(K); but the runs of a width class that
+// would only part-fill a tile are moved up into a wider class when that class's own part-filled tile has
+// room for them, so late passes with a handful of runs of different K need one tile, not one per class.
+// One CTA: the run table is staged in shared memory with coalesced loads, thread 0 does the (inherently
+// sequential, a few cycles per run) placement, all threads write the result back.
+// run_pcol[r] = packed column | W << 24 (or -1); prun/pcol are ordered by (tile, column).
 constexpr int PLAN_MAX_RUNS = 4096;
+constexpr int PLAN_CLASSES = 17;              // slot width = 4 * class, classes 1..16
 __global__ void __launch_bounds__(256)
 k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restrict__ state, int32_t* plan,
        int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol, int32_t* run_pcol) {
     __shared__ short s_k[PLAN_MAX_RUNS];        // K, or 0 when the run is not active
-    __shared__ int s_pc[PLAN_MAX_RUNS];         // packed global column or -1
-    __shared__ short s_tw[PLAN_MAX_RUNS];       // read width of the widest (= last placed) run of each tile
+    __shared__ int s_pc[PLAN_MAX_RUNS];         // packed global column | slot width << 24, or -1
+    __shared__ short s_tfirst[PLAN_MAX_RUNS];   // per tile: packed index of its first run
+    __shared__ short s_tcount[PLAN_MAX_RUNS];   // per tile: runs
+    __shared__ unsigned char s_tw[PLAN_MAX_RUNS];   // per tile: slot width
     __shared__ int s_tiles, s_np;
     for (int r = threadIdx.x; r < n_runs; r += blockDim.x)
         s_k[r] = state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] != 0 ? (short)run_k[r] : (short)0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        int tile = 0, col = 0, np = 0, cur_w = 0;
+        int cnt[PLAN_CLASSES], target[PLAN_CLASSES], stay[PLAN_CLASSES], cur_tile[PLAN_CLASSES], cur_n[PLAN_CLASSES];
+        for (int c = 0; c < PLAN_CLASSES; ++c) { cnt[c] = 0; target[c] = 0; cur_tile[c] = -1; cur_n[c] = 0; }
+        int np = 0;
+        for (int r = 0; r < n_runs; ++r)
+            if (s_k[r] > 0) { ++cnt[read_width(s_k[r]) >> 2]; ++np; }
+        // ascending: the remainder of class c moves to the narrowest wider class whose part-filled tile can take it
+        for (int c = 1; c < PLAN_CLASSES; ++c) {
+            const int cap = BN / (4 * c), rem = cnt[c] % cap;
+            if (rem == 0) continue;
+            for (int d = c + 1; d < PLAN_CLASSES; ++d) {
+                const int capd = BN / (4 * d), remd = cnt[d] % capd;
+                if (remd != 0 && remd + rem <= capd) { target[c] = d; cnt[c] -= rem; cnt[d] += rem; break; }
+            }
+        }
+        for (int c = 0; c < PLAN_CLASSES; ++c) stay[c] = cnt[c];
+        int n_tiles = 0;
         for (int r = 0; r < n_runs; ++r) {
             const int K = s_k[r];
-            int pc = -1;
+            int v = -1;
             if (K > 0) {
-                // a run owns a slot of read_width(K) columns; a tile holds slots of ONE width (runs arrive in
-                // ascending K, so a width change just closes the current tile)
-                const int w = read_width(K);
-                if (col > 0 && (col + w > BN || w != cur_w)) { ++tile; col = 0; }
-                cur_w = w;
-                pc = tile * BN + col;
-                s_tw[tile] = (short)w;
-                col += w;
-                ++np;
+                int c = read_width(K) >> 2;
+                while (stay[c] == 0 && target[c] != 0) c = target[c];   // arrivals beyond the class's share move on
+                --stay[c];
+                const int w = 4 * c;
+                if (cur_tile[c] < 0 || cur_n[c] == BN / w) {
+                    cur_tile[c] = n_tiles++;
+                    cur_n[c] = 0;
+                    s_tw[cur_tile[c]] = (unsigned char)w;
+                    s_tcount[cur_tile[c]] = 0;
+                }
+                v = (cur_tile[c] * BN + cur_n[c] * w) | (w << 24);
+                ++cur_n[c];
+                ++s_tcount[cur_tile[c]];
             }
-            s_pc[r] = pc;
+            s_pc[r] = v;
         }
-        s_tiles = np > 0 ? tile + 1 : 0;
+        int first = 0;
+        for (int t = 0; t < n_tiles; ++t) { s_tfirst[t] = (short)first; first += s_tcount[t]; }
+        s_tiles = n_tiles;
         s_np = np;
     }
     __syncthreads();
     const int n_tiles = s_tiles;
-    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) tile_count[t] = 0;
-    __syncthreads();
-    // packed index of run r = number of active runs before it: recomputed per thread chunk by a
-    // second pass of thread 0 would be serial again; instead every active run finds its rank with a
-    // block-wide inclusive scan over 256-run chunks.
-    __shared__ int s_scan[256];
-    int base = 0;
-    for (int r0 = 0; r0 < n_runs; r0 += 256) {
-        const int r = r0 + threadIdx.x;
-        const int a = (r < n_runs && s_k[r] > 0) ? 1 : 0;
-        s_scan[threadIdx.x] = a;
-        __syncthreads();
-        for (int o = 1; o < 256; o <<= 1) {
-            const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
-            __syncthreads();
-            s_scan[threadIdx.x] += v;
-            __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        tile_first[t] = (int)s_tfirst[t] | ((int)s_tw[t] << 16);
+        tile_count[t] = s_tcount[t];
+    }
+    for (int r = threadIdx.x; r < n_runs; r += blockDim.x) {
+        const int v = s_pc[r];
+        run_pcol[r] = v;
+        if (v >= 0) {
+            const int w = v >> 24, pc = v & 0xFFFFFF, t = pc / BN, col = pc - t * BN;
+            const int idx = s_tfirst[t] + col / w;
+            prun[idx] = r;
+            pcol[idx] = col | ((int)s_k[r] << 8);
         }
-        if (r < n_runs) {
-            run_pcol[r] = s_pc[r];
-            if (a) {
-                const int idx = base + s_scan[threadIdx.x] - 1;
-                const int t = s_pc[r] / BN;
-                prun[idx] = r;
-                pcol[idx] = (s_pc[r] - t * BN) | ((int)s_k[r] << 8);
-                atomicAdd(&tile_count[t], 1);
-                if (s_pc[r] == t * BN) tile_first[t] = idx | ((int)s_tw[t] << 16);   // the run that opens the tile
-            }
-        }
-        base += s_scan[255];
-        __syncthreads();
     }
     if (threadIdx.x == 0) { plan[0] = n_tiles; plan[1] = s_np; }
 }
@@ -452,10 +462,10 @@ __global__ void k_pack_centroids(const int32_t* __restrict__ run_k, const int32_
                                  const double* __restrict__ cnorm, int N, int XP, __nv_bfloat16* __restrict__ C1,
                                  __nv_bfloat16* __restrict__ C2, int NPK) {
     const int run = blockIdx.x;
-    const int pc = run_pcol[run];
-    if (pc < 0) return;
+    const int v = run_pcol[run];
+    if (v < 0) return;
     const int K = run_k[run], crow0 = run_crow0[run];
-    const int W = read_width(K);
+    const int W = v >> 24, pc = v & 0xFFFFFF;            // slot assigned by k_plan (>= read_width(K))
     for (int i = threadIdx.x; i < W * NPK; i += blockDim.x) {
         const int k = i / NPK, j = i - k * NPK;
         float v = 0.f;
