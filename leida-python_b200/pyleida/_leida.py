@@ -192,28 +192,43 @@ class Leida:
         seg_off = torch.from_numpy(segments.off).to(dev)
         seg_rows = torch.from_numpy(segments.rows).to(dev)
         self.h2d_bytes += segments.off.nbytes + segments.rows.nbytes
-        res = run_device(blocks, N, seg_off, seg_rows, K_min=self._K_min_, K_max=self._K_max_, n_init=n_init,
-                         random_state=random_state, init_indices=init_indices, centroid_update=centroid_update,
-                         keep_f64=keep_eigenvectors, comm=comm, profile=profile)
-        self.device_result_ = res
-        self.kmeans_batch_ = res.batch
-        # device -> host: labels, centroids, integer metric tables, eigenvectors
-        ks = list(range(self._K_min_, self._K_max_ + 1))
-        def to_host(t):
+        def to_host(t, stream=None):
             """device -> pinned host, asynchronous; synchronised once below"""
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
+            if stream is None:
+                h.copy_(t, non_blocking=True)
+            else:
+                with torch.cuda.stream(stream):
+                    h.copy_(t, non_blocking=True)
             return h
-        pinned = {"labels": to_host(res.labels), "occ": to_host(res.occ), "runs": to_host(res.runs),
-                  "trans": to_host(res.trans)}
+        pinned = {}
+        side = torch.cuda.Stream(device=dev) if keep_eigenvectors else None
+
+        def early_eigenvectors(lei64):
+            # the fp64 eigenvectors (the largest result) are final after stage 2: copy them out on a side
+            # stream while k-means runs
+            side.wait_stream(torch.cuda.current_stream())
+            pinned["lei"] = to_host(lei64, side)
+        res = run_device(blocks, N, seg_off, seg_rows, K_min=self._K_min_, K_max=self._K_max_, n_init=n_init,
+                         random_state=random_state, init_indices=init_indices, centroid_update=centroid_update,
+                         keep_f64=keep_eigenvectors, comm=comm, profile=profile,
+                         f64_sink=early_eigenvectors if keep_eigenvectors else None)
+        self.device_result_ = res
+        self.kmeans_batch_ = res.batch
+        # device -> host: labels (as the int64 the reference's frames hold, in both orientations: per-K rows for
+        # the models, per-volume rows for the predictions frame), centroids, integer metric tables
+        ks = list(range(self._K_min_, self._K_max_ + 1))
+        labels64 = res.labels.to(torch.int64)
+        pinned.update({"labels": to_host(labels64), "labels_t": to_host(labels64.t().contiguous()),
+                       "occ": to_host(res.occ), "runs": to_host(res.runs), "trans": to_host(res.trans)})
         for k in ks:
             pinned[f"c{k}"] = to_host(res.models[k].centers_device_)
-        if keep_eigenvectors:
-            pinned["lei"] = to_host(res.lei64)
         torch.cuda.current_stream().synchronize()
-        labels = pinned["labels"].numpy()
+        if side is not None:
+            side.synchronize()
+        labels, labels_t = pinned["labels"].numpy(), pinned["labels_t"].numpy()
         occ, runs, trans = pinned["occ"].numpy(), pinned["runs"].numpy(), pinned["trans"].numpy()
-        self.d2h_bytes += labels.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
+        self.d2h_bytes += labels.nbytes + labels_t.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
         sc = None
         if scores and comm.world == 1:                     # Dunn / silhouette / Davies-Bouldin (_clustering.py:331-339)
             from .clustering.kmeans import score_sample, sweep_runs
@@ -227,14 +242,14 @@ class Leida:
         models, perf = {}, []
         for c, k in enumerate(ks):
             km = res.models[k]
-            km.labels_ = labels[c].astype(np.int64)
+            km.labels_ = labels[c]
             km.cluster_centers_ = pinned[f"c{k}"].numpy().copy()
             self.d2h_bytes += km.cluster_centers_.nbytes
             models[f"k_{k}"] = km
             perf.append({"k": k, "Dunn_score": sc["Dunn_score"][c] if sc else np.nan, "distortion": km.inertia_,
                          "silhouette_score": sc["silhouette_score"][c] if sc else np.nan,
                          "Davies-Bouldin_score": sc["Davies-Bouldin_score"][c] if sc else np.nan})
-        predictions = pd.concat([predictions, pd.DataFrame(labels.T.astype(np.int64), columns=[f"k_{k}" for k in ks])], axis=1)
+        predictions = pd.concat([predictions, pd.DataFrame(labels_t, columns=[f"k_{k}" for k in ks], copy=False)], axis=1)
         self._lei_host = None
         if keep_eigenvectors:
             self._lei_host = pinned["lei"].numpy()         # stays in the pinned buffer (no second copy)
@@ -246,7 +261,11 @@ class Leida:
         self._clustering_ = Bunch(predictions=predictions, performance=pd.DataFrame(perf), models=models)
         self._dynamics_ = Bunch(dwell_times=dynamics["dwell_times"], occupancies=dynamics["occupancies"],
                                 transitions=dynamics["transitions"], stats=None)
-        self._classes_lst_ = np.unique(cond_list.astype(str)).tolist()
+        # np.unique(eigenvectors.condition) (_leida.py:190) without touching the per-volume column: the labels a
+        # subject contributes are classes[s][1:n_volumes+1] (one per volume) or its single label
+        used = [c for s_, nv_ in zip(ids, n_vols)
+                for c in (self.classes[s_][1:nv_ + 1] if len(self.classes[s_]) > 1 else self.classes[s_][:1])]
+        self._classes_lst_ = np.unique(np.asarray(used).astype(str)).tolist()
         self._N_classes_ = len(self._classes_lst_)
 
     # ------------------------------------------------------------------------------------------

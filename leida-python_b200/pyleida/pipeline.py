@@ -20,9 +20,11 @@ class DeviceResult:
 
 
 def run_device(blocks, n_rois, seg_off, seg_rows, K_min=2, K_max=20, n_init=15, random_state=None,
-               init_indices=None, centroid_update="exact", keep_f64=True, comm=None, profile=None):
+               init_indices=None, centroid_update="exact", keep_f64=True, comm=None, profile=None, f64_sink=None):
     """blocks: list of CUDA fp64 tensors (S_b, N, T_b), subjects in pipeline order.
     seg_off / seg_rows: CUDA int64 tensors describing the metric groups (see Segments).
+    f64_sink: optional callable(lei64) invoked right after the stage-1/2 launches are queued; `Leida`
+    uses it to start the device->host copy of the fp64 eigenvectors on a side stream while k-means runs.
     Returns a DeviceResult; nothing is copied to the host except the few control words k-means
     needs (active-run count, per-run distortion and cluster sizes for restart selection)."""
     torch = nv.require_cuda()
@@ -39,6 +41,8 @@ def run_device(blocks, n_rois, seg_off, seg_rows, K_min=2, K_max=20, n_init=15, 
         leading_eigenvectors(b, want_f64=keep_f64, out_f64=None if lei64 is None else lei64[r0:r0 + nr],
                              out_f32=x32[r0:r0 + nr])
         r0 += nr
+    if f64_sink is not None and lei64 is not None:
+        f64_sink(lei64)
     off = row_offsets(comm.all_gather_int(M))
     engine = KMeansEngine(x32, n_features=N, comm=comm, row_lo=int(off[comm.rank]), m_global=int(off[-1]))
     runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices)

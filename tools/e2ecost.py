@@ -13,9 +13,10 @@ for rep in range(4):
     if rep == 3:
         pr = cProfile.Profile(); pr.enable()
     m = pyleida.Leida.from_arrays(ts, classes)
-    m.fit_predict(TR=0.72, K_min=2, K_max=20, n_init=15, init_indices=inits, keep_eigenvectors=True, scores=(rep % 2 == 1))
+    m.fit_predict(TR=0.72, K_min=2, K_max=20, n_init=15, init_indices=inits, keep_eigenvectors=True, scores=False)
     if rep == 3:
         pr.disable()
     torch.cuda.synchronize(); t1 = time.perf_counter()
     print(f"rep{rep} scores={rep % 2 == 1}: fit_predict {1e3*(t1-t0):.1f} ms  h2d {m.h2d_bytes/1e6:.0f} MB d2h {m.d2h_bytes/1e6:.0f} MB")
-pstats.Stats(pr).sort_stats("tottime").print_stats(18)
+pstats.Stats(pr).sort_stats("tottime").print_stats(28)
+pstats.Stats(pr).sort_stats("cumtime").print_stats(35)
