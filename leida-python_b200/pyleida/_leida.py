@@ -24,7 +24,7 @@ def _staging_pool():
     global _POOL
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=4)
+        _POOL = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4))
     return _POOL
 
 
@@ -161,17 +161,21 @@ class Leida:
             host = torch.empty((j - i, N, T), dtype=torch.float64, pin_memory=True)
             hv = host.numpy()
             dev_block = torch.empty((j - i, N, T), dtype=torch.float64, device=dev)
-            # stage in slices: worker threads fill pinned memory (numpy copies release the GIL) while
-            # the previous slice is already on its way over PCIe
+            # stage in slices: worker threads fill pinned memory (numpy copies release the GIL); all fills are
+            # queued at once and every slice goes over PCIe as soon as its own fills are done
             step = max(1, (j - i + 7) // 8)
 
             def fill(lo, hi, base=i):
                 for b in range(lo, hi):
                     hv[b] = self.time_series[ids[base + b]]
+            pool, pending = _staging_pool(), []
             for lo in range(0, j - i, step):
                 hi = min(j - i, lo + step)
-                parts = np.array_split(np.arange(lo, hi), min(4, hi - lo))
-                list(_staging_pool().map(lambda p: fill(int(p[0]), int(p[-1]) + 1), [p for p in parts if len(p)]))
+                cuts = np.linspace(lo, hi, min(4, hi - lo) + 1).astype(int)
+                pending.append((lo, hi, [pool.submit(fill, int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]))
+            for lo, hi, futs in pending:
+                for f in futs:
+                    f.result()
                 dev_block[lo:hi].copy_(host[lo:hi], non_blocking=True)
             blocks.append(dev_block)
             self.h2d_bytes += host.numel() * 8
