@@ -219,7 +219,7 @@ def reference_arm(args):
         "gpu_launches": 0,
         "stage_seconds_sample": {k: float(np.mean([r[k] for r in times])) for k in ("stage12", "kmeans", "metrics")},
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
@@ -235,7 +235,6 @@ def native_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keeps NCCL's version banner out of the JSON on stdout
         dist.init_process_group("nccl", device_id=dev)
     import pyleida
     from pyleida import _native as nvl
@@ -408,14 +407,33 @@ def native_arm(args):
                        f"{n_init_sample} of {wl['n_init']} restarts per K (k-means time scaled x{wl['n_init'] / n_init_sample:g}), "
                        f"runs spread over {cores} processes; {times[0]['wall']:.1f} s of CPU wall time")}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_RESULT_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    # Libraries print to stdout on their own (NCCL's version banner at communicator creation): route
+    # everything that is not the result line to stderr.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -222,6 +222,17 @@ int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_cro
                         float* cent, double* cnorm, int64_t* state, int n_iter,
                         int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
                         int32_t* mailbox, leida_stream_t stream);
+/* Same, with the all-reduce fused in (several GPUs of one node): peer_bufs is a DEVICE array of n_peers
+ * pointers, one per rank (this rank included), each to that rank's exchange buffer -- its acc words
+ * followed, from word state_offset_words, by its state words -- mapped into this process (CUDA IPC /
+ * symmetric memory).  The kernel reads the buffers in place over NVLink and sums them (int64: exact, order
+ * free), and only for the runs that are still active.  The caller orders the ranks: every rank's buffer is
+ * complete before any rank's call starts, and is not rewritten before every rank's call has finished. */
+int leida_kmeans_update_peers(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                              const int64_t* const* peer_bufs, int n_peers, int64_t state_offset_words,
+                              float* cent, double* cnorm, int64_t* state, int n_iter,
+                              int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
+                              int32_t* mailbox, leida_stream_t stream);
 /* n_active_out: device int32[8], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
  * [2] = runs still active after this call, [3] = calls completed, [4] = first all-stopped call).  mailbox (may be NULL): HOST-visible (pinned, mapped)
  * int32[4]; the last CTA stores {runs still active, number of update calls completed, index of the

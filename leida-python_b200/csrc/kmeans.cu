@@ -409,20 +409,44 @@ __global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
 }
 
 // Control + centroid update, one CTA per run.
+// Where k_update reads the job-wide sums from: one buffer (single GPU, or after an NCCL all-reduce), or the
+// exchange buffers of all ranks, read in place over NVLink and summed here (int64: exact, any order) -- the
+// all-reduce fused into its consumer, and only for the runs that are still active.
+struct ReducedSource {
+    const long long* acc;             // n_peers == 0
+    const long long* state;
+    const long long* const* peers;    // n_peers > 0: device array of every rank's buffer (acc words, then state words)
+    int n_peers;
+    long long state_off;
+    __device__ __forceinline__ long long sum(long long word) const {
+        long long v = 0;
+        for (int p = 0; p < n_peers; ++p) v += *reinterpret_cast<const volatile long long*>(peers[p] + word);
+        return v;
+    }
+    __device__ __forceinline__ long long acc_word(long long i) const { return n_peers ? sum(i) : acc[i]; }
+    __device__ __forceinline__ long long state_word(long long i) const { return n_peers ? sum(state_off + i) : state[i]; }
+};
+
 __global__ void __launch_bounds__(256)
 k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int N, int XP,
-         const long long* __restrict__ acc_red, const long long* __restrict__ state_red, float* cent, double* cnorm,
+         const ReducedSource red, float* cent, double* cnorm,
          long long* state, int n_iter, int32_t* n_active, const int32_t* __restrict__ run_pcol,
          __nv_bfloat16* __restrict__ C1, __nv_bfloat16* __restrict__ C2, int NPK, volatile int32_t* mailbox) {
     const int run = blockIdx.x;
     long long* st = state + (long long)run * kStateWords;
     __shared__ int s_go;
     __shared__ int s_empty;
+    __shared__ long long s_cnt[LEIDA_KM_MAX_K];
     const int K = run_k[run], crow0 = run_crow0[run];
     const int AP = XP + 8;
-    // every thread checks one cluster for emptiness (needed only if the run continues)
+    const bool was_active = st[LEIDA_KM_ST_ACTIVE] != 0;        // block-uniform; only thread 0 writes it, later
+    // every thread fetches one cluster's member count (and checks it for emptiness)
     int my_empty = 0;
-    if (threadIdx.x < K && acc_red[(long long)(crow0 + threadIdx.x) * AP + XP] <= 0) my_empty = 1;
+    if (was_active && threadIdx.x < K) {
+        const long long c = red.acc_word((long long)(crow0 + threadIdx.x) * AP + XP);
+        s_cnt[threadIdx.x] = c;
+        if (c <= 0) my_empty = 1;
+    }
     const int any_empty = __syncthreads_or(my_empty);
     if (threadIdx.x == 0) {
         int go = 0;
@@ -430,16 +454,16 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
         if (st[LEIDA_KM_ST_ACTIVE] != 0) {
             const long long p = st[LEIDA_KM_ST_PASSES];  // index of the pass that just finished
             st[LEIDA_KM_ST_PASSES] = p + 1;
-            const long long changed = state_red[(long long)run * kStateWords + LEIDA_KM_ST_CHANGED];
+            const long long changed = red.state_word((long long)run * kStateWords + LEIDA_KM_ST_CHANGED);
             st[LEIDA_KM_ST_CHANGED_TOTAL] += changed;
-            st[LEIDA_KM_ST_RECHECK_TOTAL] += state_red[(long long)run * kStateWords + LEIDA_KM_ST_RECHECKED];
+            st[LEIDA_KM_ST_RECHECK_TOTAL] += red.state_word((long long)run * kStateWords + LEIDA_KM_ST_RECHECKED);
             // pass p >= 1 is Lloyd iteration p-1; the reference tests convergence from iteration 1 on
             // (clustering/_clustering.py:129-132) and runs at most n_iter iterations (:118).
             if ((p >= 2 && changed == 0) || p >= n_iter) st[LEIDA_KM_ST_ACTIVE] = 0;
             else go = 1;
             if (go && any_empty) {
                 for (int k = 0; k < K; ++k)
-                    if (acc_red[(long long)(crow0 + k) * AP + XP] <= 0) { s_empty = k + 1; break; }
+                    if (s_cnt[k] <= 0) { s_empty = k + 1; break; }
                 st[LEIDA_KM_ST_EMPTY] = s_empty;
                 st[LEIDA_KM_ST_ACTIVE] = 0;
                 go = 0;
@@ -457,8 +481,8 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             const int k = i / XP, j = i - k * XP;
             float v = 0.f;
             if (j < N) {
-                const long long cnt = acc_red[(long long)(crow0 + k) * AP + XP];
-                const double sum = (double)acc_red[(long long)(crow0 + k) * AP + j] * (1.0 / kFracScale);
+                const long long cnt = s_cnt[k];
+                const double sum = (double)red.acc_word((long long)(crow0 + k) * AP + j) * (1.0 / kFracScale);
                 v = (float)(sum / (double)cnt);
             }
             cent[(long long)(crow0 + k) * XP + j] = v;
@@ -836,22 +860,42 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
     return check_launch("k_recheck");
 }
 
-extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
-                                   const int64_t* acc_reduced, const int64_t* state_reduced, float* cent, double* cnorm,
-                                   int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol, void* C1,
-                                   void* C2, int32_t* mailbox, leida_stream_t stream) {
+static int launch_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                         const ReducedSource& red, float* cent, double* cnorm, int64_t* state, int n_iter,
+                         int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2, int32_t* mailbox,
+                         leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    LEIDA_REQUIRE(run_k && run_crow0 && acc_reduced && state_reduced && cent && cnorm && state && n_active_out, "null pointer");
+    LEIDA_REQUIRE(run_k && run_crow0 && cent && cnorm && state && n_active_out, "null pointer");
     int rc = check_runs(n_runs, N, x_pitch);
     if (rc) return rc;
     LEIDA_REQUIRE(n_iter >= 0, "n_iter >= 0");
     LEIDA_CUDA_TRY(cudaMemsetAsync(n_active_out, 0, sizeof(int32_t), st));
     LEIDA_REQUIRE((run_pcol == nullptr) == (C1 == nullptr) && (C1 == nullptr) == (C2 == nullptr), "run_pcol, C1, C2 together");
     const int NPK = (int)(((int64_t)N + 1 + 63) / 64 * 64);     // = leida_kmeans_tc_pitch(N)
-    k_update<<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, (const long long*)acc_reduced,
-                                     (const long long*)state_reduced, cent, cnorm, (long long*)state, n_iter, n_active_out,
-                                     run_pcol, (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK, mailbox);
+    k_update<<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, red, cent, cnorm, (long long*)state, n_iter,
+                                     n_active_out, run_pcol, (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK, mailbox);
     return check_launch("k_update");
+}
+
+extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                                   const int64_t* acc_reduced, const int64_t* state_reduced, float* cent, double* cnorm,
+                                   int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol, void* C1,
+                                   void* C2, int32_t* mailbox, leida_stream_t stream) {
+    LEIDA_REQUIRE(acc_reduced && state_reduced, "null pointer");
+    ReducedSource red{(const long long*)acc_reduced, (const long long*)state_reduced, nullptr, 0, 0};
+    return launch_update(n_runs, run_k, run_crow0, N, x_pitch, red, cent, cnorm, state, n_iter, n_active_out, run_pcol,
+                         C1, C2, mailbox, stream);
+}
+
+extern "C" int leida_kmeans_update_peers(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N,
+                                         int64_t x_pitch, const int64_t* const* peer_bufs, int n_peers,
+                                         int64_t state_offset_words, float* cent, double* cnorm, int64_t* state,
+                                         int n_iter, int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
+                                         int32_t* mailbox, leida_stream_t stream) {
+    LEIDA_REQUIRE(peer_bufs && n_peers >= 1 && n_peers <= 64 && state_offset_words > 0, "peer buffers");
+    ReducedSource red{nullptr, nullptr, (const long long* const*)peer_bufs, n_peers, (long long)state_offset_words};
+    return launch_update(n_runs, run_k, run_crow0, N, x_pitch, red, cent, cnorm, state, n_iter, n_active_out, run_pcol,
+                         C1, C2, mailbox, stream);
 }
 
 extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch, int n_runs,

@@ -11,7 +11,7 @@ import warnings
 import numpy as np
 
 from .. import _native as nv
-from ..parallel import Comm, gather_seed_rows
+from ..parallel import Comm, PeerExchange, gather_seed_rows
 from ..signal_tools.phase import padded_pitch
 
 _KP_BUCKETS = (4, 8, 12, 16, 20, 24, 32, 40, 48, 64)
@@ -143,6 +143,7 @@ class KMeansEngine:
         mb = mailbox.numpy()
         st = nv.stream()
 
+        peers = None
         if self.comm.world > 1:
             seed_rows = gather_seed_rows(self.X, self.N, seeds_global, self.row_lo, self.comm)
             init_idx = torch.arange(CR, dtype=torch.int64, device=dev)
@@ -151,6 +152,9 @@ class KMeansEngine:
             red_global = torch.empty_like(red_local)
             acc_red = red_global[:n_acc].view(CR, AP)
             state_red = red_global[n_acc:].view(R, nv.STATE_WORDS)
+            # per-pass exchange: peer-memory reads fused into leida_kmeans_update_peers when the ranks can map
+            # each other's buffers, else copy + NCCL all-reduce into red_global
+            peers = PeerExchange.get(self.comm, red_local.numel(), dev) if centroid_update == "exact" else None
         else:
             init_idx = torch.from_numpy(seeds_global).to(dev)
             nv.call("leida_kmeans_init", nv.ptr(self.X), self.XP, nv.ptr(init_idx), R, nv.ptr(run_k), nv.ptr(run_c0),
@@ -223,6 +227,14 @@ class KMeansEngine:
                     "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(grid_bound[0]), nv.ptr(plan),
                     nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
                     nv.ptr(state), stq))
+            if self.comm.world > 1 and peers is not None:
+                ptrs = peers.publish(red_local)
+                timed("update", lambda: nv.call(
+                    "leida_kmeans_update_peers", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(ptrs),
+                    peers.world, n_acc, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
+                    nv.ptr(run_pcol) if tc else None, nv.ptr(c1) if tc else None, nv.ptr(c2) if tc else None,
+                    mailbox.data_ptr(), stq))
+                return
             if self.comm.world > 1:
                 red_global.copy_(red_local)
                 self.comm.all_reduce_sum_(red_global)

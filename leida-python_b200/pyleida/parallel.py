@@ -74,3 +74,65 @@ def gather_seed_rows(X_local, n_cols, global_rows, row_lo, comm):
         out[mine] = X_local[(idx[mine] - row_lo)]
     comm.all_reduce_sum_(out)
     return out
+
+
+class PeerExchange:
+    """Double-buffered int64 exchange buffer in symmetric memory (torch.distributed._symmetric_memory):
+    every rank of the node maps every other rank's buffer, so `leida_kmeans_update_peers` can read the
+    partial centroid sums of all ranks in place over NVLink -- the per-pass all-reduce fused into the
+    kernel that consumes it.  One pass = publish(local words) [device copy into this pass's
+    half + a cross-rank barrier on the stream] -> kernel reads `ptrs()`.  Two halves alternate, so a rank
+    that is one pass ahead never overwrites what a slower rank is still reading: it cannot be two passes
+    ahead because every pass has a barrier.
+
+    get() is collective.  It returns None on every rank if any rank cannot set the mapping up (no
+    symmetric-memory support, ranks on different nodes, LEIDA_EXCHANGE=nccl); the caller then uses the
+    NCCL all-reduce.  Buffers are cached per (group, device) and reused by later engines."""
+    _cache = {}
+
+    def __init__(self, words, dev, group):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        self.words = int(words)
+        self.buf = symm.empty(2 * self.words, dtype=torch.int64, device=dev)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.world = int(self.hdl.world_size)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self._ptrs = [torch.tensor([b + h * self.words * 8 for b in base], dtype=torch.int64, device=dev) for h in (0, 1)]
+        self.half = 0
+
+    @classmethod
+    def get(cls, comm, words, dev):
+        import os
+        import torch
+        if comm.world <= 1 or dev.type != "cuda":
+            return None
+        dist = comm._dist
+        group = comm.group if comm.group is not None else dist.group.WORLD
+        key = (group.group_name, dev.index)
+        ex = cls._cache.get(key)
+        ok = 1
+        if os.environ.get("LEIDA_EXCHANGE", "peer") != "peer":
+            ok = 0
+        elif ex is None or ex.words < words:
+            try:
+                ex = cls(max(int(words), 1 << 19), dev, group)
+            except Exception as e:                      # noqa: BLE001 - any failure means "use NCCL"
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce")
+                ex, ok = None, 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
+        if int(flag.item()) == 0:
+            return None
+        cls._cache[key] = ex
+        return ex
+
+    def publish(self, local_words):
+        """Copy this rank's words into the current half and order it against every rank (on the current
+        stream).  Returns the device array of per-rank pointers to that half."""
+        h = self.half
+        self.half ^= 1
+        self.buf[h * self.words: h * self.words + local_words.numel()].copy_(local_words)
+        self.hdl.barrier(channel=0)
+        return self._ptrs[h]
