@@ -24,7 +24,9 @@ def _staging_pool():
     global _POOL
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4))
+        # several ranks on one host share its cores (torchrun exports LOCAL_WORLD_SIZE)
+        per_rank = (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, per_rank)))
     return _POOL
 
 

@@ -86,8 +86,12 @@ class PeerExchange:
     ahead because every pass has a barrier.
 
     get() is collective.  It returns None on every rank if any rank cannot set the mapping up (no
-    symmetric-memory support, ranks on different nodes, LEIDA_EXCHANGE=nccl); the caller then uses the
-    NCCL all-reduce.  Buffers are cached per (group, device) and reused by later engines."""
+    symmetric-memory support, ranks on different nodes) or if the mode says NCCL; the caller then uses the
+    NCCL all-reduce.  LEIDA_EXCHANGE = peer | nccl | auto (default).  auto = peer reads for 2 ranks, NCCL
+    for more: in-place reads move (world-1) x the payload per rank and need a full cross-rank barrier per
+    pass, NCCL moves ~2x the payload.  Measured on B200 / NVSwitch (config 2 per GPU, ms per step):
+    2 GPUs 82.0 peer vs 85.6 NCCL; 8 GPUs 87.9 peer vs 81.5 NCCL (also when only the late passes with few
+    active runs use the peer path: 87.8).  Buffers are cached per (group, device) and reused by later engines."""
     _cache = {}
 
     def __init__(self, words, dev, group):
@@ -112,7 +116,8 @@ class PeerExchange:
         key = (group.group_name, dev.index)
         ex = cls._cache.get(key)
         ok = 1
-        if os.environ.get("LEIDA_EXCHANGE", "peer") != "peer":
+        mode = os.environ.get("LEIDA_EXCHANGE", "auto")
+        if mode == "nccl" or (mode != "peer" and comm.world > 2):
             ok = 0
         elif ex is None or ex.words < words:
             try:
