@@ -206,11 +206,14 @@ int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64
                            const int32_t* prun, const int32_t* pcol, const int32_t* run_k, const int32_t* run_crow0,
                            int32_t* labels_new, int64_t* state, int32_t* worklist, int64_t worklist_cap,
                            leida_stream_t stream);
-int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs_bound,
+int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int unit_rows, int n_runs_bound,
                           const int32_t* plan, const int32_t* prun,
                           const int32_t* run_k, const int32_t* run_crow0,
                           int32_t* labels_cur, const int32_t* labels_new, int64_t* acc, int64_t* state,
                           leida_stream_t stream);
+
+/* unit_rows != 0: the caller guarantees |X[i][j]| <= 1 for every element (true for LEiDA eigenvectors); the
+ * kernel may then quantise on the FMA pipe.  Results are the same integers either way. */
 
 /* Convergence bookkeeping + centroid update of every active run (clustering/_clustering.py:118-133):
  * a run stops when a pass at Lloyd iteration >= 1 changed no label, or after n_iter iterations;

@@ -491,17 +491,63 @@ __global__ void k_pack_centroids(const int32_t* __restrict__ run_k, const int32_
 // global int64 atomic per (cluster, column) it touched.  Integer sums: any grouping gives the same result.
 constexpr int APPLY_ROWS = 4096;
 constexpr int APPLY_THREADS = 256;
+constexpr int APPLY_DIRECT_MAX = 32;      // changed rows per (chunk, run) up to which the unsorted path is used
 
 __device__ __forceinline__ long long quant40(float v) { return __double2ll_rn((double)v * 1099511627776.0); }
 
+// Sum over the listed rows of quant40(x[row]) = rne(x * 2^40).  ncu (profiles/r01_k_diff_apply_ncu.txt): in the
+// dense early passes the kernel is bound by instruction issue and by the conversion pipe (F2F + F2I.S64 per
+// element, 16 lanes/clk/SM), not by memory.  So: the gather address is a 32-bit product (local row < 4096,
+// pitch < 2^19) on one 64-bit base, eight loads are issued before the first value is used, and -- when the
+// caller guarantees |x| <= 1 (UNIT: LEiDA eigenvectors are unit vectors) -- half of the elements are quantised
+// on the FMA pipe instead: with h = rne(x * 2^20) and r = x - h * 2^-20 (exact, |r| <= 2^-21),
+// x * 2^40 = h * 2^20 + r * 2^40 exactly and the first term is an even integer, so
+// rne(x * 2^40) = h * 2^20 + rne(r * 2^40); both roundings are one fp32 fma onto 1.5 * 2^23, whose bit pattern
+// is 0x4B400000 + the integer.  The bit patterns are summed as they are in 32-bit wrap-around arithmetic and
+// the offsets removed every 512 elements (|sum h| <= 2^29).  Same integers as quant40 (checked exhaustively
+// enough on the host: 2e8 random bit patterns and the tie / denormal / +-1 edge cases).
+template <bool UNIT>
+__device__ __forceinline__ long long quant_sum(const float* __restrict__ xb, unsigned j, unsigned XP,
+                                               const unsigned short* __restrict__ rows, int e0, int e1, int stride) {
+    constexpr float MAGIC = 12582912.f;           // 1.5 * 2^23
+    constexpr uint32_t MAGIC_BITS = 0x4B400000u;
+    long long total = 0;
+    int e = e0;
+    while (e + 7 * stride < e1) {
+        uint32_t sh = 0, sl = 0, nb = 0;
+        for (; nb < 128 && e + 7 * stride < e1; ++nb, e += 8 * stride) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(xb + ((unsigned)rows[e + u * stride] * XP + j));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (UNIT && (u & 1)) {
+                    const float th = fmaf(v[u], 1048576.f, MAGIC);                 // MAGIC + h
+                    const float r = fmaf(th - MAGIC, -9.5367431640625e-07f, v[u]); // x - h * 2^-20
+                    const float tl = fmaf(r, 1099511627776.f, MAGIC);              // MAGIC + rne(r * 2^40)
+                    sh += __float_as_uint(th);
+                    sl += __float_as_uint(tl);
+                } else {
+                    total += quant40(v[u]);
+                }
+            }
+        }
+        if (UNIT)
+            total += ((long long)(int)(sh - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl - 4u * nb * MAGIC_BITS);
+    }
+    for (; e < e1; e += stride) total += quant40(__ldg(xb + ((unsigned)rows[e] * XP + j)));
+    return total;
+}
+
+template <bool UNIT>
 __global__ void __launch_bounds__(APPLY_THREADS)
 k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ plan,
              const int32_t* __restrict__ prun, const int32_t* __restrict__ run_k,
              const int32_t* __restrict__ run_crow0, int32_t* __restrict__ labels_cur,
              const int32_t* __restrict__ labels_new, long long* acc, long long* state) {
     __shared__ int s_list[APPLY_ROWS];       // local row | old<<16 | new<<24
-    __shared__ short s_in[APPLY_ROWS];       // local rows sorted by NEW cluster
-    __shared__ short s_out[APPLY_ROWS];      // local rows sorted by OLD cluster (old >= 0 only)
+    __shared__ unsigned short s_in[APPLY_ROWS];       // local rows sorted by NEW cluster
+    __shared__ unsigned short s_out[APPLY_ROWS];      // local rows sorted by OLD cluster (old >= 0 only)
     __shared__ int s_cin[LEIDA_KM_MAX_K + 1], s_cout[LEIDA_KM_MAX_K + 1], s_pin[LEIDA_KM_MAX_K], s_pout[LEIDA_KM_MAX_K];
     __shared__ int s_n;
     const int AP = XP + 8;
@@ -543,6 +589,30 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     __syncthreads();
     const int nchg = s_n;
     if (nchg == 0) continue;
+    if (nchg <= APPLY_DIRECT_MAX) {
+        // Few changes in this chunk (the late passes): the sorted path below would walk K clusters one after
+        // the other with a dependent gather each; instead every (changed row, column) pair is handled by its
+        // own thread -- independent loads, two global atomics (enter / leave).
+        const float* xb = X + row_base * XP;
+        for (int e = threadIdx.x; e < nchg * N; e += APPLY_THREADS) {
+            const int i = e / N, j = e - i * N;
+            const int v = s_list[i];
+            const int o = (v >> 16) & 0xff, n = (v >> 24) & 0xff;
+            const long long q = quant40(__ldg(xb + ((unsigned)(v & 0xffff) * (unsigned)XP + (unsigned)j)));
+            atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + n) * AP + j), (unsigned long long)q);
+            if (o != 0xff)
+                atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + o) * AP + j), (unsigned long long)(-q));
+        }
+        if (threadIdx.x < K) {
+            const int d = s_cin[threadIdx.x] - s_cout[threadIdx.x];
+            if (d != 0)
+                atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + threadIdx.x) * AP + XP), (unsigned long long)(long long)d);
+        }
+        if (threadIdx.x == 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(state + (long long)run * kStateWordsTc + LEIDA_KM_ST_CHANGED),
+                      (unsigned long long)nchg);
+        continue;
+    }
     if (threadIdx.x == 0) {          // exclusive prefix sums (K <= 64)
         int a = 0, b = 0;
         for (int k = 0; k < K; ++k) {
@@ -557,8 +627,8 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     for (int e = threadIdx.x; e < nchg; e += APPLY_THREADS) {
         const int v = s_list[e];
         const int o = (v >> 16) & 0xff, n = (v >> 24) & 0xff;
-        s_in[atomicAdd(&s_pin[n], 1)] = (short)(v & 0xffff);
-        if (o != 0xff) s_out[atomicAdd(&s_pout[o], 1)] = (short)(v & 0xffff);
+        s_in[atomicAdd(&s_pin[n], 1)] = (unsigned short)(v & 0xffff);
+        if (o != 0xff) s_out[atomicAdd(&s_pout[o], 1)] = (unsigned short)(v & 0xffff);
     }
     __syncthreads();
     const int CW = N >= APPLY_THREADS ? APPLY_THREADS : ((N + 31) & ~31);
@@ -566,15 +636,13 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
     const int g = threadIdx.x / CW, j0 = threadIdx.x - g * CW;
     if (g < groups) {
         const float* xb = X + row_base * XP;
+        asm volatile("" : "+l"(xb));     // one 64-bit base register: element address = one IMAD.WIDE on a 32-bit index
         for (int k = 0; k < K; ++k) {
             const int ib = s_cin[k], ie = s_cin[k + 1], ob = s_cout[k], oe = s_cout[k + 1];
             if (ib == ie && ob == oe) continue;
             for (int j = j0; j < N; j += CW) {
-                long long sum = 0;
-#pragma unroll 4
-                for (int e = ib + g; e < ie; e += groups) sum += quant40(xb[(long long)s_in[e] * XP + j]);
-#pragma unroll 4
-                for (int e = ob + g; e < oe; e += groups) sum -= quant40(xb[(long long)s_out[e] * XP + j]);
+                const long long sum = quant_sum<UNIT>(xb, (unsigned)j, (unsigned)XP, s_in, ib + g, ie, groups) -
+                                      quant_sum<UNIT>(xb, (unsigned)j, (unsigned)XP, s_out, ob + g, oe, groups);
                 if (sum != 0)
                     atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + k) * AP + j), (unsigned long long)sum);
             }
@@ -701,15 +769,20 @@ extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const floa
     return check_launch("k_tc_assign");
 }
 
-extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int n_runs_bound,
+extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int unit_rows, int n_runs_bound,
                                      const int32_t* plan, const int32_t* prun, const int32_t* run_k,
                                      const int32_t* run_crow0, int32_t* labels_cur, const int32_t* labels_new,
                                      int64_t* acc, int64_t* state, leida_stream_t stream) {
     LEIDA_REQUIRE(X && plan && prun && run_k && run_crow0 && labels_cur && labels_new && acc && state, "null pointer");
-    LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && n_runs_bound >= 1 && n_runs_bound <= 65535, "sizes");
+    LEIDA_REQUIRE(M >= 1 && N >= 1 && x_pitch >= N && x_pitch < (1 << 19) && n_runs_bound >= 1 && n_runs_bound <= 65535, "sizes");
     dim3 grid((unsigned)(n_runs_bound < 48 ? n_runs_bound : 48), (unsigned)((M + APPLY_ROWS - 1) / APPLY_ROWS));
-    k_diff_apply<<<grid, APPLY_THREADS, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, plan, prun, run_k, run_crow0,
-                                                                   labels_cur, labels_new, (long long*)acc,
-                                                                   (long long*)state);
+    if (unit_rows)
+        k_diff_apply<true><<<grid, APPLY_THREADS, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, plan, prun, run_k, run_crow0,
+                                                                             labels_cur, labels_new, (long long*)acc,
+                                                                             (long long*)state);
+    else
+        k_diff_apply<false><<<grid, APPLY_THREADS, 0, (cudaStream_t)stream>>>(X, M, N, (int)x_pitch, plan, prun, run_k, run_crow0,
+                                                                              labels_cur, labels_new, (long long*)acc,
+                                                                              (long long*)state);
     return check_launch("k_diff_apply");
 }

@@ -61,6 +61,8 @@ class KMeansEngine:
         self.m_global = int(m_global) if m_global is not None else self.M
         self.xnorm = torch.empty(max(self.M, 1), dtype=torch.float64, device=X.device)
         nv.call("leida_kmeans_row_norms", nv.ptr(X), self.M, N, xp, nv.ptr(self.xnorm), nv.stream())
+        # |x| <= 1 everywhere (LEiDA eigenvectors are unit vectors) lets leida_kmeans_tc_apply quantise on the FMA pipe
+        self.unit_rows = bool(self.M > 0 and float(X.abs().max()) <= 1.0)
 
     # ------------------------------------------------------------------------------------------
     def _tc_operands(self):
@@ -224,7 +226,7 @@ class KMeansEngine:
                     nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
                     nv.ptr(worklist), cap, nv.ptr(labels_new), stq))
                 timed("apply", lambda: nv.call(
-                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(grid_bound[0]), nv.ptr(plan),
+                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(self.unit_rows), int(grid_bound[0]), nv.ptr(plan),
                     nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
                     nv.ptr(state), stq))
             if self.comm.world > 1 and peers is not None:
