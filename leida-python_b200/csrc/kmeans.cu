@@ -869,7 +869,6 @@ static int launch_update(int n_runs, const int32_t* run_k, const int32_t* run_cr
     int rc = check_runs(n_runs, N, x_pitch);
     if (rc) return rc;
     LEIDA_REQUIRE(n_iter >= 0, "n_iter >= 0");
-    LEIDA_CUDA_TRY(cudaMemsetAsync(n_active_out, 0, sizeof(int32_t), st));
     LEIDA_REQUIRE((run_pcol == nullptr) == (C1 == nullptr) && (C1 == nullptr) == (C2 == nullptr), "run_pcol, C1, C2 together");
     const int NPK = (int)(((int64_t)N + 1 + 63) / 64 * 64);     // = leida_kmeans_tc_pitch(N)
     k_update<<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, red, cent, cnorm, (long long*)state, n_iter,
