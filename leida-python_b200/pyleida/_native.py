@@ -107,5 +107,17 @@ def call(name, *args):
     check(getattr(lib, name)(*args), name)
 
 
+def prepared(name, *args):
+    """A zero-argument callable for a call whose arguments never change (the per-pass launches of the k-means
+    loop): the symbol lookup and the argument tuple are built once, so issuing it costs one ctypes call."""
+    fn = getattr(lib, name)
+
+    def run():
+        rc = fn(*args)
+        if rc != 0:
+            check(rc, name)
+    return run
+
+
 def launch_count():
     return int(lib.leida_launch_count())

@@ -163,6 +163,8 @@ class KMeansEngine:
                     self.N, self.XP, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), self.M, nv.ptr(state), st)
             acc_red, state_red = acc, state
 
+        capturing = [False]      # True while _capture() records the launches on its side stream
+
         def timed(name, fn):
             if profile is None or not (profile.get("*") or name in profile):
                 return fn()
@@ -200,13 +202,21 @@ class KMeansEngine:
                 groups.append((g0, i, int(ks[g0:i].max())))
                 g0 = i
 
+        # The launches of a pass never change their arguments (except the apply grid bound after a re-plan), and in
+        # the late passes the GPU needs less time for a pass than Python needs to marshal four calls: bind them once.
+        fast = {}
+
         def do_assign():
-            stq = nv.stream()
+            stq = st if not capturing[0] else nv.stream()
             if tc:
-                nv.call("leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
+                f = fast.get(("assign", stq))
+                if f is None:
+                    f = fast[("assign", stq)] = nv.prepared(
+                        "leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
                         self.N, nv.ptr(c1), nv.ptr(c2), c_rows, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(plan), nv.ptr(tile_first),
                         nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels_new),
                         nv.ptr(state), nv.ptr(worklist), cap, stq)
+                f()
                 return
             for (a, b, kmax) in groups:
                 nv.call("leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
@@ -219,16 +229,22 @@ class KMeansEngine:
                         nv.ptr(worklist), cap, None, stq)
 
         def do_rest():
-            stq = nv.stream()
+            stq = st if not capturing[0] else nv.stream()
             if tc:
-                timed("recheck", lambda: nv.call(
-                    "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
-                    nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
-                    nv.ptr(worklist), cap, nv.ptr(labels_new), stq))
-                timed("apply", lambda: nv.call(
-                    "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(self.unit_rows), int(grid_bound[0]), nv.ptr(plan),
-                    nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
-                    nv.ptr(state), stq))
+                f = fast.get(("recheck", stq))
+                if f is None:
+                    f = fast[("recheck", stq)] = nv.prepared(
+                        "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
+                        nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
+                        nv.ptr(worklist), cap, nv.ptr(labels_new), stq)
+                timed("recheck", f)
+                f = fast.get(("apply", stq, grid_bound[0]))
+                if f is None:
+                    f = fast[("apply", stq, grid_bound[0])] = nv.prepared(
+                        "leida_kmeans_tc_apply", nv.ptr(self.X), self.M, self.N, self.XP, int(self.unit_rows), int(grid_bound[0]),
+                        nv.ptr(plan), nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
+                        nv.ptr(state), stq)
+                timed("apply", f)
             if self.comm.world > 1 and peers is not None:
                 ptrs = peers.publish(red_local)
                 timed("update", lambda: nv.call(
@@ -240,11 +256,14 @@ class KMeansEngine:
             if self.comm.world > 1:
                 red_global.copy_(red_local)
                 self.comm.all_reduce_sum_(red_global)
-            timed("update", lambda: nv.call(
-                "leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
-                nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
-                nv.ptr(run_pcol) if tc else None, nv.ptr(c1) if tc else None, nv.ptr(c2) if tc else None,
-                mailbox.data_ptr(), stq))
+            f = fast.get(("update", stq))
+            if f is None:
+                f = fast[("update", stq)] = nv.prepared(
+                    "leida_kmeans_update", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(acc_red),
+                    nv.ptr(state_red), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
+                    nv.ptr(run_pcol) if tc else None, nv.ptr(c1) if tc else None, nv.ptr(c2) if tc else None,
+                    mailbox.data_ptr(), stq)
+            timed("update", f)
             if centroid_update == "reference":
                 nv.call("leida_kmeans_means_f32_sequential", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_k),
                         nv.ptr(run_c0), nv.ptr(labels), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm), stq)
@@ -277,7 +296,9 @@ class KMeansEngine:
                 if not use_graph:
                     grid_bound[0] = max(1, packed_bound)
             if use_graph and issued == 1 and not eager_rest:
+                capturing[0] = True
                 graphs = self._capture(do_assign, do_rest, split=time_assign)
+                capturing[0] = False
             if graphs is None:
                 timed("assign", do_assign)
                 do_rest()
