@@ -272,7 +272,7 @@ def native_arm(args):
         flush.zero_()
         m = pyleida.Leida.from_arrays(ts, classes, comm=comm)
         m.fit_predict(TR=wl["TR"], K_min=wl["K_min"], K_max=wl["K_max"], n_init=wl["n_init"], init_indices=inits,
-                      keep_eigenvectors=True, scores=False)     # the metric covers phase->eigvec->k-means->metrics
+                      keep_eigenvectors=True, scores=False, stats=False)     # the metric covers phase->eigvec->k-means->metrics
         # consume the result like a user would: labels of every K are already host arrays; the metric
         # DataFrames are assembled on access -- touch the three tables of one K
         k = wl["K_max"]

@@ -307,6 +307,36 @@ int leida_dynamics_counts_i32(const int32_t* labels, int64_t label_pitch, int n_
                               const int64_t* seg_off, const int64_t* seg_rows, int n_segments, int kmax,
                               int32_t* occ, int32_t* runs, int32_t* trans, leida_stream_t stream);
 
+/* ---- post-hoc statistics (reference: pyleida/stats/_stats.py:54-269) ------------------------
+ * The two-group tests the reference runs on every column of the occupancy / dwell-time tables after the hot
+ * path (permtest_ind, permtest_rel, hedges_g; _compute_stats :275-364, called from _leida.py:336-342),
+ * batched over variables x permutations.  values: device fp64 (n_rows, n_vars) row-major table; idx1 / idx2:
+ * device int32 row indices of the two groups.
+ *
+ * leida_stats_moments_f64: out[var][8] = {mean1, mean2, sum of squared deviations 1, 2, Levene W
+ *   (scipy.stats.levene center='mean', :102), n1, n2, 0}; hedges_g (:135-192) and the Levene p-value follow
+ *   from these on the host.
+ * leida_perm_ttest_ind_f64: t_obs[var] = scipy.stats.ttest_ind statistic (pooled when equal_var[var], else
+ *   Welch); counts[var][3] = number of permuted splits with t <= t_obs, t >= t_obs, |t| >= |t_obs|
+ *   (the comparisons of SciPy's _permutation_ttest, which ttest_ind(permutations=) ran, :105-111).
+ *   perms == NULL: n_perm uniformly random splits drawn on the device (Philox4x32-10 keyed by seed, selection
+ *   sampling).  perms != NULL: int32 (n_perm, n1+n2) index permutations of the pooled sample (group 1 first),
+ *   e.g. all C(n1+n2, n1) splits for an exact test.  null_out (may be NULL): fp64 (n_vars, n_perm).
+ * leida_perm_paired_f64: obs[var] = mean(x1) - mean(x2) over the n pairs (idx1[i], idx2[i]);
+ *   counts[var][2] = number of permutations with statistic <= obs + g, >= obs - g, g = 100 eps |obs|
+ *   (scipy.stats.permutation_test permutation_type='samples', :236-244).  swaps == NULL: every pair swapped
+ *   with probability 1/2 on the device; swaps != NULL: uint8 (n_perm, n), 1 = swap.
+ * Limits: n1, n2 >= 2 (independent), n1 + n2 <= 4096, n <= 4096. */
+int leida_stats_moments_f64(const double* values, int64_t n_rows, int n_vars, const int32_t* idx1, int n1,
+                            const int32_t* idx2, int n2, double* out, leida_stream_t stream);
+int leida_perm_ttest_ind_f64(const double* values, int64_t n_rows, int n_vars, const int32_t* idx1, int n1,
+                             const int32_t* idx2, int n2, const uint8_t* equal_var, int n_perm,
+                             const int32_t* perms, uint64_t seed, double* t_obs, int32_t* counts,
+                             double* null_out, leida_stream_t stream);
+int leida_perm_paired_f64(const double* values, int64_t n_rows, int n_vars, const int32_t* idx1,
+                          const int32_t* idx2, int n, int n_perm, const uint8_t* swaps, uint64_t seed,
+                          double* obs, int32_t* counts, double* null_out, leida_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,10 +104,11 @@ class Leida:
     # ------------------------------------------------------------------------------------------
     def fit_predict(self, TR=None, paired_tests=False, n_perm=5_000, save_results=False, random_state=None,
                     K_min=2, K_max=20, n_init=15, init_indices=None, centroid_update="exact",
-                    keep_eigenvectors=True, scores=True, _profile=None):
+                    keep_eigenvectors=True, scores=True, stats=True, _profile=None):
         """_leida.py:111-192.  K range and n_init are arguments here (the reference hard-codes
-        2..20 and 15, :156-157 / _clustering.py:250); paired_tests / n_perm are validated like the
-        reference but the statistics stage is not run; save_results=True writes the reference's
+        2..20 and 15, :156-157 / _clustering.py:250); stats=True runs the permutation tests on the occupancy and
+        dwell-time tables like the reference (_leida.py:336-342; on the GPU, stats/_stats.py) when there are at least
+        two conditions with two rows each, on single-GPU runs; save_results=True writes the reference's
         'LEiDA_results' folder layout (results_io.py) and, like the reference, refuses to overwrite it.  scores=True
         fills the Dunn / silhouette / Davies-Bouldin columns of the performance table like the reference
         (they are not part of the benchmarked hot path; single-GPU only)."""
@@ -132,6 +133,7 @@ class Leida:
         self._K_min_, self._K_max_ = int(K_min), int(K_max)
         self._execute_all(TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, _profile, scores)
         self._is_fitted = True
+        self._run_stats(stats, paired_tests, n_perm, random_state)
         if save_results:                                                                   # _leida.py:306-310 and the stage writers
             from .results_io import save_clustering, save_dynamics, save_eigenvectors
             save_eigenvectors(self._results_path_, self.eigenvectors)
@@ -139,6 +141,9 @@ class Leida:
             save_dynamics(self._results_path_, {"occupancies": self._dynamics_.occupancies,
                                                 "dwell_times": self._dynamics_.dwell_times,
                                                 "transitions": self._dynamics_.transitions})
+            if self._dynamics_.get("stats") is not None:
+                from .results_io import save_stats
+                save_stats(self._results_path_, self._dynamics_["stats"])
         return self
 
     def _execute_all(self, TR, random_state, n_init, init_indices, centroid_update, keep_eigenvectors, profile=None,
@@ -273,6 +278,33 @@ class Leida:
                 for c in (self.classes[s_][1:nv_ + 1] if len(self.classes[s_]) > 1 else self.classes[s_][:1])]
         self._classes_lst_ = np.unique(np.asarray(used).astype(str)).tolist()
         self._N_classes_ = len(self._classes_lst_)
+
+    def _run_stats(self, stats, paired_tests, n_perm, random_state):
+        """Stage 4b of the reference (_leida.py:336-342): permutation tests per state and K.  The tables are tested as
+        they are (one row per subject and condition); results are kept in memory, `save_results` writes them with the
+        other dynamics files."""
+        if not stats:
+            return
+        comm = self._comm if self._comm is not None else Comm()
+        if comm.world > 1:
+            warnings.warn("the statistics stage needs every subject on one GPU; skipped on multi-GPU runs")
+            return
+        first = self._dynamics_.occupancies[f"k_{self._K_min_}"]
+        sizes = first.groupby("condition").size()
+        if len(sizes) < 2 or int(sizes.min()) < 2:
+            return                                   # nothing to compare (the reference would fail inside scipy here)
+        if paired_tests and len(set(sizes.tolist())) != 1:
+            raise ValueError("paired_tests=True needs the same number of rows in every condition")
+        from .stats import _compute_stats
+        tables = {"occupancies": self._dynamics_.occupancies, "dwell_times": self._dynamics_.dwell_times}
+        self._dynamics_["stats"] = _compute_stats(tables, paired_tests=paired_tests, n_perm=n_perm, save_results=False,
+                                                  random_state=random_state if isinstance(random_state, int) else None)
+
+    def stats(self, k=2, metric="occupancies"):
+        """Results of the statistical analysis for the K partition (_leida.py:475-500)."""
+        if self._dynamics_.get("stats") is None:
+            raise Exception("the statistics stage was not run (stats=False, a single condition, or a multi-GPU run)")
+        return self._dynamics_["stats"][metric][f"k_{k}"]
 
     # ------------------------------------------------------------------------------------------
     @property

@@ -186,8 +186,13 @@ class LazyFrames(dict):
     """{'k_K': DataFrame} whose DataFrames are assembled on first access from the exact integer
     tables (the arithmetic is already done; pandas object construction is the expensive part)."""
 
-    def __init__(self, builders):
+    def __init__(self, builders, raw=None, conditions=None):
+        """raw: optional {key: callable -> (values ndarray, column names)} and conditions: the per-row condition
+        labels -- the numbers behind the frames, for consumers that do not need pandas objects (the statistics
+        stage)."""
         super().__init__()
+        self.raw = raw
+        self.conditions = conditions
         self._builders = dict(builders)
         for k in self._builders:
             dict.__setitem__(self, k, None)
@@ -278,10 +283,15 @@ def compute_dynamics_metrics(clusters_labels, TR=None, save_results=False, path=
 def tables_from_counts(names, col_k, seg, occ, runs, trans, TR=None):
     """The reference's three DataFrames per K column from the integer tables of dynamics_counts()."""
     lengths = np.diff(seg.off)
-    b_occ, b_dw, b_tr = {}, {}, {}
+    b_occ, b_dw, b_tr, r_occ, r_dw = {}, {}, {}, {}, {}
     for i, name in enumerate(names):
         k = int(col_k[i])
-        b_occ[name] = lambda i=i, k=k: _state_frame(seg, _occupancy(occ[i][:, :k], lengths), k)
-        b_dw[name] = lambda i=i, k=k: _state_frame(seg, _dwell(occ[i][:, :k], runs[i][:, :k], TR), k)
+        cols = [f"PL_state_{j + 1}" for j in range(k)]
+        r_occ[name] = lambda i=i, k=k, cols=cols: (_occupancy(occ[i][:, :k], lengths), cols)
+        r_dw[name] = lambda i=i, k=k, cols=cols: (_dwell(occ[i][:, :k], runs[i][:, :k], TR), cols)
+        b_occ[name] = lambda name=name, k=k: _state_frame(seg, r_occ[name]()[0], k)
+        b_dw[name] = lambda name=name, k=k: _state_frame(seg, r_dw[name]()[0], k)
         b_tr[name] = lambda i=i, k=k: _transition_frame(seg, _transitions(trans[i][:, :k, :k]), k)
-    return {"dwell_times": LazyFrames(b_dw), "occupancies": LazyFrames(b_occ), "transitions": LazyFrames(b_tr)}
+    cond = seg.conditions_array()
+    return {"dwell_times": LazyFrames(b_dw, r_dw, cond), "occupancies": LazyFrames(b_occ, r_occ, cond),
+            "transitions": LazyFrames(b_tr)}

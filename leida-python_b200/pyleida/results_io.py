@@ -34,6 +34,15 @@ def save_dynamics(path, metrics):
             table.to_csv(os.path.join(root, k, fname), sep="\t", index=False)
 
 
+def save_stats(path, stats):
+    """{metric}_stats.csv next to the metric tables (stats/_stats.py:356-359)."""
+    root = os.path.join(path, "dynamics_metrics")
+    for metric, per_k in stats.items():
+        for k, table in per_k.items():
+            os.makedirs(os.path.join(root, k), exist_ok=True)
+            table.to_csv(os.path.join(root, k, f"{metric}_stats.csv"), sep="\t", index=False)
+
+
 def save_eigenvectors(path, eigenvectors):
     os.makedirs(path, exist_ok=True)
     eigenvectors.to_csv(os.path.join(path, "eigenvectors.csv"), sep="\t", index=False)

@@ -174,11 +174,43 @@ def stability_case():
     np.savez_compressed(os.path.join(OUT, "stability_case.npz"), **out)
 
 
+def stats_case():
+    """permtest_ind / permtest_rel / hedges_g (stats/_stats.py:54-269) on the occupancy and dwell-time tables of
+    the pipeline case plus a synthetic 2-condition table with a real effect and unequal variances.  The reference
+    functions run unmodified except for the ttest_ind signature shim (ref_shim._compat_ttest_ind): statistic,
+    Levene decision ('test'), effect size, Bonferroni alpha are the reference's; p-values are random (unseeded in
+    the reference) and are stored only as a plausibility band."""
+    import contextlib, io
+    rng = np.random.default_rng(11)
+    n1, n2, nv = 23, 31, 7
+    vals = np.vstack([rng.normal(0.30, 1.0, (n1, nv)), rng.normal(0.0, 1.0, (n2, nv))])
+    vals[n1:, 2] *= 2.5                      # unequal variances -> Welch
+    vals[:n1, 4] += 1.2                      # a clear effect
+    cond = np.array(["patients"] * n1 + ["controls"] * n2)
+    cols = [f"PL_state_{i + 1}" for i in range(nv)]
+    df = pd.DataFrame(vals, columns=cols)
+    df.insert(0, "condition", cond)
+    with contextlib.redirect_stdout(io.StringIO()):
+        np.random.seed(3)
+        ind = ref.permtest_ind(df, class_column="condition", n_perm=5000, alternative="two-sided")
+        half = min(n1, n2)
+        dfp = pd.concat([df.iloc[:half], df.iloc[n1:n1 + half]])
+        rel = ref.permtest_rel(dfp, class_column="condition", n_perm=5000, alternative="two-sided")
+    out = {"values": vals, "condition": cond.astype("U"), "columns": np.array(cols, dtype="U"), "half": np.int64(half)}
+    for name, t in (("ind", ind), ("rel", rel)):
+        for c in t.columns:
+            v = t[c].values
+            v = np.asarray(v)
+            out[f"{name}_{c}"] = v if v.dtype.kind in "biuf" else np.array([str(x) for x in v], dtype="U")
+    np.savez_compressed(os.path.join(OUT, "stats_case.npz"), **out)
+
+
 if __name__ == "__main__":
     signal_cases()
     kmeans_cases()
     metric_cases()
     pipeline_case()
     stability_case()
+    stats_case()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -30,6 +30,22 @@ _STUBS = [
 ]
 
 
+def _compat_ttest_ind(a, b, alternative="two-sided", permutations=None, equal_var=True, **kwargs):
+    """Stand-in for the `ttest_ind(..., permutations=n)` signature of SciPy 1.7 - 1.14 that the reference calls
+    (stats/_stats.py:105-111) and the installed SciPy removed.  Observed statistic: the installed
+    scipy.stats.ttest_ind.  Permutation p-value: the restatement of that SciPy's `_permutation_ttest` in
+    oracle/leida_oracle.py -- so for THAT number the reference run is not an independent check (the oracle
+    header says "parity unpinned" for it); everything else permtest_ind returns is the reference's own."""
+    from types import SimpleNamespace
+    from scipy import stats
+    import leida_oracle
+    res = stats.ttest_ind(a, b, equal_var=equal_var, alternative=alternative)
+    if not permutations:
+        return res
+    _, p, _ = leida_oracle.permutation_ttest_ind(a, b, int(permutations), equal_var, alternative)
+    return SimpleNamespace(statistic=res.statistic, pvalue=p)
+
+
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "pyleida"))
 
@@ -54,6 +70,13 @@ def load_reference():
         st = importlib.import_module("pyleida.signal_tools._signal_tools")
         cl = importlib.import_module("pyleida.clustering._clustering")
         dm = importlib.import_module("pyleida.dynamics_metrics._dynamics_metrics")
+        try:
+            # stats/_stats.py imports `ttest_ind, levene, ks_2samp, permutation_test` from scipy.stats; all exist, but
+            # permtest_ind passes `permutations=` to ttest_ind, which the installed SciPy no longer accepts.
+            sm = importlib.import_module("pyleida.stats._stats")
+            sm.ttest_ind = _compat_ttest_ind
+        except Exception:                         # noqa: BLE001 - the stats row is optional for the hot-path tests
+            sm = None
     finally:
         sys.path.remove(REFERENCE_ROOT)
         ref_mods = {k: v for k, v in sys.modules.items() if k == "pyleida" or k.startswith("pyleida.")}
@@ -74,6 +97,10 @@ def load_reference():
         transition_probabilities=dm.transition_probabilities,
         transition_probabilities_group=dm.transition_probabilities_group,
         compute_dynamics_metrics=dm.compute_dynamics_metrics,
+        hedges_g=getattr(sm, "hedges_g", None),
+        permtest_ind=getattr(sm, "permtest_ind", None),
+        permtest_rel=getattr(sm, "permtest_rel", None),
+        compute_stats=getattr(sm, "_compute_stats", None),
         _modules=(st, cl, dm),
     )
     return ns

@@ -540,3 +540,110 @@ def test_centroids_distances(P, O):
     assert np.array_equal(np.argmin(d.iloc[:, 2:].values, axis=1), m.predictions["k_3"].values)
     with pytest.raises(ValueError):
         m.centroids_distances(9)
+
+
+# ---- post-hoc statistics -------------------------------------------------------------------
+
+def _stats_frame(g):
+    import pandas as pd
+    df = pd.DataFrame(g["values"], columns=[str(c) for c in g["columns"]])
+    df.insert(0, "condition", [str(c) for c in g["condition"]])
+    return df
+
+
+def test_permtest_ind_golden_and_identical_permutations(P, O):
+    """permtest_ind on the GPU against the fixture made by the unmodified reference (statistic, Levene decision,
+    effect size, alpha, table layout) and against the oracle on IDENTICAL permutations: the whole null distribution
+    and the p-values must agree (for every alternative)."""
+    g = np.load(os.path.join(GOLD, "stats_case.npz"))
+    df = _stats_frame(g)
+    n = len(df)
+    n1 = int((df.condition == "controls").sum())               # np.unique order: 'controls' is group 1
+    rng = np.random.RandomState(12)
+    perms = np.asarray([rng.permutation(n) for _ in range(3000)])
+    res, null = P.stats.permtest_ind(df, class_column="condition", n_perm=3000, perms=perms, return_null=True)
+    assert list(res.columns) == ["variable", "group_1", "group_2", "statistic", "p-value", "test", "effect_size",
+                                 "alpha_Bonferroni", "reject_null"]
+    for j in range(len(res)):
+        assert res["variable"][j] == str(g["ind_variable"][j]) and res["test"][j] == str(g["ind_test"][j])
+        assert res["group_1"][j] == str(g["ind_group_1"][j]) and res["group_2"][j] == str(g["ind_group_2"][j])
+        assert res["statistic"][j] == pytest.approx(g["ind_statistic"][j], rel=1e-12)
+        assert res["effect_size"][j] == pytest.approx(g["ind_effect_size"][j], rel=1e-12)
+        assert res["alpha_Bonferroni"][j] == g["ind_alpha_Bonferroni"][j]
+    vals, cond = g["values"], np.asarray([str(c) for c in g["condition"]])
+    for alt in ("two-sided", "less", "greater"):
+        got = P.stats.permtest_ind(df, class_column="condition", n_perm=3000, perms=perms, alternative=alt)
+        for j, c in enumerate(res["variable"]):
+            x1, x2 = vals[cond == "controls", j], vals[cond == "patients", j]
+            _, p, ref_null = O.permutation_ttest_ind(x1, x2, 3000, res["test"][j] == "t-test", alt, perms=perms)
+            if alt == "two-sided":
+                assert np.allclose(null[j], ref_null, rtol=1e-10, atol=1e-12), j
+            assert got["p-value"][j] == pytest.approx(p, abs=1.5 / 3001), (alt, j)    # a tie at fp64 rounding may flip one count
+    assert n1 == 31
+
+
+def test_permtest_ind_device_rng_and_exact_branch(P, O):
+    """Device-drawn splits: reproducible for a seed, different for another, and statistically equal to the oracle's
+    p-values (6 standard errors); groups small enough to enumerate give the exact test, equal to the oracle's."""
+    import pandas as pd
+    g = np.load(os.path.join(GOLD, "stats_case.npz"))
+    df = _stats_frame(g)
+    a = P.stats.permtest_ind(df, class_column="condition", n_perm=5000, random_state=7)
+    b = P.stats.permtest_ind(df, class_column="condition", n_perm=5000, random_state=7)
+    c = P.stats.permtest_ind(df, class_column="condition", n_perm=5000, random_state=8)
+    assert np.array_equal(a["p-value"].values, b["p-value"].values)
+    assert not np.array_equal(a["p-value"].values, c["p-value"].values)
+    for j in range(len(a)):
+        p = float(g["ind_p-value"][j])
+        assert abs(a["p-value"][j] - p) <= 6 * np.sqrt(max(p * (1 - p), 1e-3) / 5000) * 1.5, j
+    rng = np.random.default_rng(3)
+    small = pd.DataFrame(rng.normal(size=(9, 3)), columns=["s1", "s2", "s3"])
+    small.insert(0, "condition", ["x"] * 5 + ["y"] * 4)
+    got = P.stats.permtest_ind(small, class_column="condition", n_perm=5000)        # C(9,5) = 126 splits: exact
+    rows = O.permtest_table(small.iloc[:, 1:].values, small.condition.values, ["s1", "s2", "s3"], n_perm=5000)
+    for j, r in enumerate(rows):
+        assert got["p-value"][j] == pytest.approx(r["p-value"], abs=1e-15)
+        assert got["statistic"][j] == pytest.approx(r["statistic"], rel=1e-12)
+
+
+def test_permtest_rel_and_compute_stats(P, O):
+    """Paired test: statistic / effect size against the reference fixture, null distribution against the oracle on
+    identical swaps, exact branch for few pairs; _compute_stats returns the reference's nested layout."""
+    import pandas as pd
+    g = np.load(os.path.join(GOLD, "stats_case.npz"))
+    df = _stats_frame(g)
+    half = int(g["half"])
+    n1 = int((df.condition == "patients").sum())
+    dfp = pd.concat([df.iloc[:half], df.iloc[n1:n1 + half]]).reset_index(drop=True)
+    rng = np.random.default_rng(4)
+    swaps = rng.integers(0, 2, size=(2000, half))
+    res, null = P.stats.permtest_rel(dfp, class_column="condition", n_perm=2000, swaps=swaps, return_null=True)
+    assert list(res.columns) == ["variable", "group_1", "group_2", "statistic", "p-value", "effect_size",
+                                 "alpha_Bonferroni", "reject_null"]
+    vals, cond = dfp.iloc[:, 1:].values, dfp.condition.values
+    for j in range(len(res)):
+        assert res["statistic"][j] == pytest.approx(g["rel_statistic"][j], rel=1e-12, abs=1e-15)
+        assert res["effect_size"][j] == pytest.approx(g["rel_effect_size"][j], rel=1e-12)
+        x1, x2 = vals[cond == "controls", j], vals[cond == "patients", j]
+        _, p, ref_null = O.permutation_paired(x1, x2, 2000, swaps=swaps)
+        assert np.allclose(null[j], ref_null, rtol=1e-10, atol=1e-13), j
+        assert res["p-value"][j] == pytest.approx(p, abs=1e-15)
+    few = pd.concat([dfp.iloc[:6], dfp.iloc[half:half + 6]])
+    ex = P.stats.permtest_rel(few, class_column="condition", n_perm=5000)                 # 2^6 = 64 sign patterns: exact
+    fv, fc = few.iloc[:, 1:].values, few.condition.values
+    for j in range(len(ex)):
+        _, p, _ = O.permutation_paired(fv[fc == "controls", j], fv[fc == "patients", j], 5000)
+        assert ex["p-value"][j] == pytest.approx(p, abs=1e-15)
+    # _compute_stats on a fitted model's tables (two conditions)
+    from pyleida import synthetic
+    ts, classes = synthetic.make_dataset(12, 20, 90, "states")
+    m = P.Leida.from_arrays(ts, classes).fit_predict(TR=0.72, K_min=2, K_max=4, n_init=2, random_state=0, n_perm=200, scores=False)
+    t = m.stats(3, "occupancies")
+    assert list(t.columns)[:2] == ["k", "variable"] and len(t) == 3 and int(t["k"][0]) == 3
+    assert set(m._dynamics_["stats"].keys()) == {"dwell_times", "occupancies"}
+    occ = m.occupancies(3)
+    mine = O.permtest_table(occ.iloc[:, 2:].values, occ.condition.values, list(occ.columns[2:]), n_perm=200,
+                            random_state=np.random.RandomState(0))
+    for j, r in enumerate(mine):
+        assert t["statistic"][j] == pytest.approx(r["statistic"], rel=1e-11)
+        assert t["test"][j] == r["test"] and t["effect_size"][j] == pytest.approx(r["effect_size"], rel=1e-11)

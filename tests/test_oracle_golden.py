@@ -113,3 +113,48 @@ def test_clustering_scores_match_reference_table():
         assert sc["Dunn_score"] == pytest.approx(g["perf_dunn"][i], rel=1e-6)
         assert sc["silhouette_score"] == pytest.approx(g["perf_silhouette"][i], abs=1e-6)
         assert sc["Davies-Bouldin_score"] == pytest.approx(g["perf_db"][i], rel=1e-9)
+
+
+def test_stats_fixture_matches_oracle():
+    """tests/golden/stats_case.npz (made by the unmodified reference's permtest_ind / permtest_rel, see
+    oracle/make_golden.py: stats_case): statistic, Levene decision, effect size, Bonferroni alpha are reproduced by
+    the oracle; the stored p-values (random in the reference) lie within 6 standard errors of the oracle's."""
+    g = np.load(os.path.join(GOLD, "stats_case.npz"))
+    vals, cond, cols = g["values"], g["condition"], [str(c) for c in g["columns"]]
+    rows = O.permtest_table(vals, cond, cols, n_perm=5000, random_state=np.random.RandomState(9))
+    for j, r in enumerate(rows):
+        assert str(g["ind_variable"][j]) == r["variable"] and str(g["ind_test"][j]) == r["test"]
+        assert str(g["ind_group_1"][j]) == r["group_1"] and str(g["ind_group_2"][j]) == r["group_2"]
+        assert g["ind_statistic"][j] == pytest.approx(r["statistic"], rel=1e-13)
+        assert g["ind_effect_size"][j] == r["effect_size"]
+        assert g["ind_alpha_Bonferroni"][j] == r["alpha_Bonferroni"]
+        p = r["p-value"]
+        assert abs(g["ind_p-value"][j] - p) <= 6 * np.sqrt(max(p * (1 - p), 1e-3) / 5000)
+    half = int(g["half"])
+    n1 = int((cond == "patients").sum())
+    sel = np.r_[0:half, n1:n1 + half]
+    rel = O.permtest_table(vals[sel], cond[sel], cols, n_perm=5000, paired=True, random_state=np.random.default_rng(1))
+    for j, r in enumerate(rel):
+        assert g["rel_statistic"][j] == pytest.approx(r["statistic"], rel=1e-13, abs=1e-16)
+        assert g["rel_effect_size"][j] == r["effect_size"]
+        p = r["p-value"]
+        assert abs(g["rel_p-value"][j] - p) <= 12 * np.sqrt(max(p * (1 - p), 1e-3) / 5000)
+
+
+def test_permutation_tests_exact_branch_equals_scipy():
+    """Small groups: every split is enumerated; the oracle's p-values equal the installed SciPy's exact tests
+    (ttest_ind with PermutationMethod; permutation_test permutation_type='samples')."""
+    from scipy import stats
+    rng = np.random.default_rng(2)
+    a, b = rng.normal(size=5), rng.normal(0.5, 1.0, size=4)
+    for alt in ("two-sided", "less", "greater"):
+        mine = O.permutation_ttest_ind(a, b, 5000, True, alt)[1]
+        ref = stats.ttest_ind(a, b, alternative=alt, method=stats.PermutationMethod(n_resamples=5000)).pvalue
+        if alt != "two-sided":          # SciPy's current two-sided p is 2 min(less, greater); the 1.9-1.14 one is |t| >= |t_obs|
+            assert mine == pytest.approx(ref, abs=1e-15)
+    e1, e2 = rng.normal(size=8), rng.normal(size=8)
+    for alt in ("two-sided", "less", "greater"):
+        mine = O.permutation_paired(e1, e2, 5000, alt)[1]
+        ref = stats.permutation_test((e1, e2), lambda x, y, axis: np.mean(x, axis=axis) - np.mean(y, axis=axis), n_resamples=5000,
+                                     vectorized=True, permutation_type="samples", alternative=alt).pvalue
+        assert mine == pytest.approx(ref, abs=1e-15)

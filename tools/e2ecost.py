@@ -13,7 +13,7 @@ for rep in range(4):
     if rep == 3:
         pr = cProfile.Profile(); pr.enable()
     m = pyleida.Leida.from_arrays(ts, classes)
-    m.fit_predict(TR=0.72, K_min=2, K_max=20, n_init=15, init_indices=inits, keep_eigenvectors=True, scores=False)
+    m.fit_predict(TR=0.72, K_min=2, K_max=20, n_init=15, init_indices=inits, keep_eigenvectors=True, scores=False, stats=False)
     if rep == 3:
         pr.disable()
     torch.cuda.synchronize(); t1 = time.perf_counter()

@@ -13,7 +13,7 @@ times = []
 for rep in range(9):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     m = pyleida.Leida.from_arrays(ts, classes)
-    m.fit_predict(TR=0.72, K_min=2, K_max=20, n_init=15, init_indices=inits, keep_eigenvectors=True, scores=False)
+    m.fit_predict(TR=0.72, K_min=2, K_max=20, n_init=15, init_indices=inits, keep_eigenvectors=True, scores=False, stats=False)
     _ = m.occupancies(5)
     torch.cuda.synchronize(); t1 = time.perf_counter()
     times.append(1e3 * (t1 - t0)); del m
