@@ -70,7 +70,7 @@ def _levene_p(W, n1, n2):
     return betainc(dfd / 2.0, 0.5, dfd / (dfd + W))            # F(1, dfd) survival function
 
 
-def _ind_core(vals, cls, n_perm, alternative, random_state, perms=None, return_null=False):
+def _ind_core(vals, cls, n_perm, alternative, random_state, perms=None, return_null=False, adjustment="biased"):
     """All columns of `vals` (rows, n_vars) in one batch: arrays of statistic, p-value, equal_var flag, effect size."""
     torch = nv.require_cuda()
     groups, d_vals, d1, d2, dev = _to_device(vals, cls)
@@ -95,7 +95,7 @@ def _ind_core(vals, cls, n_perm, alternative, random_state, perms=None, return_n
             n_used, nv.ptr(d_perms), _seed(random_state), nv.ptr(t_obs), nv.ptr(counts), nv.ptr(null), nv.stream())
     t_obs, counts = t_obs.cpu().numpy(), counts.cpu().numpy()
     col = {"less": 0, "greater": 1}.get(alternative, 2)
-    adj = 0 if exact else 1                                     # randomised test: biased estimate (SciPy >= 1.9)
+    adj = 0 if (exact or adjustment == "none") else 1         # randomised test: biased estimate (SciPy >= 1.9)
     pvals = (counts[:, col] + adj) / (n_used + adj)
     var1, var2 = mom[:, 2] / n1, mom[:, 3] / n2                 # np.var (ddof = 0), as hedges_g uses
     eff = np.abs(mom[:, 0] - mom[:, 1]) / np.sqrt(((n1 - 1) * var1 + (n2 - 1) * var2) / (n1 + n2 - 2))
@@ -154,14 +154,16 @@ def _table(core, features, lo, hi, paired):
 
 
 def permtest_ind(data, class_column=None, n_perm=5_000, alternative="two-sided", random_state=None, perms=None,
-                 return_null=False):
+                 return_null=False, adjustment="biased"):
     """Permutation t-test (pooled or Welch, chosen per column by Levene's test) of two independent groups for
     every feature column of `data`, with Hedges's g and a Bonferroni-corrected alpha (stats/_stats.py:54-133).
-    perms: optional (n, n1+n2) index permutations of the pooled sample (group 1 first) used for every column."""
+    perms: optional (n, n1+n2) index permutations of the pooled sample (group 1 first) used for every column.
+    adjustment: "biased" -> p = (b + 1) / (m + 1) for a randomised test (SciPy >= 1.9); "none" -> b / m (SciPy 1.8,
+    the version the reference's environment.yml pins)."""
     _validate(data, class_column, n_perm)
     features = [c for c in data if c != class_column]
     core = _ind_core(data[features].to_numpy(dtype=np.float64), np.asarray(data[class_column].values), n_perm, alternative,
-                     random_state, perms, return_null)
+                     random_state, perms, return_null, adjustment)
     res = _table(core, features, 0, len(features), paired=False)
     return (res, core["null"]) if return_null else res
 
