@@ -382,25 +382,36 @@ __global__ void k_split_rows(const float* __restrict__ X, long long M, int N, lo
 // sequential, a few cycles per run) placement, all threads write the result back.
 // run_pcol[r] = packed column | W << 24 (or -1); prun/pcol are ordered by (tile, column).
 constexpr int PLAN_MAX_RUNS = 4096;
+constexpr int PLAN_MAX_TILES = PLAN_MAX_RUNS / 2;   // widest slot = 64 columns = two runs per tile
 constexpr int PLAN_CLASSES = 17;              // slot width = 4 * class, classes 1..16
 __global__ void __launch_bounds__(256)
 k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restrict__ state, int32_t* plan,
        int32_t* tile_first, int32_t* tile_count, int32_t* prun, int32_t* pcol, int32_t* run_pcol) {
     __shared__ short s_k[PLAN_MAX_RUNS];        // K, or 0 when the run is not active
     __shared__ int s_pc[PLAN_MAX_RUNS];         // packed global column | slot width << 24, or -1
-    __shared__ short s_tfirst[PLAN_MAX_RUNS];   // per tile: packed index of its first run
-    __shared__ short s_tcount[PLAN_MAX_RUNS];   // per tile: runs
-    __shared__ unsigned char s_tw[PLAN_MAX_RUNS];   // per tile: slot width
+    __shared__ short s_tfirst[PLAN_MAX_TILES];  // per tile: packed index of its first run
+    __shared__ short s_tcount[PLAN_MAX_TILES];  // per tile: runs
+    __shared__ unsigned char s_tw[PLAN_MAX_TILES];  // per tile: slot width
+    __shared__ unsigned char s_cls[PLAN_MAX_RUNS];  // width class (slot width / 4) of the run, 0 when not active
+    __shared__ int s_cnt[PLAN_CLASSES];
     __shared__ int s_tiles, s_np;
-    for (int r = threadIdx.x; r < n_runs; r += blockDim.x)
-        s_k[r] = state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] != 0 ? (short)run_k[r] : (short)0;
+    if (threadIdx.x < PLAN_CLASSES) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    // everything that is per run and order free happens in parallel; thread 0 only does the ordered placement
+    for (int r = threadIdx.x; r < n_runs; r += blockDim.x) {
+        const int K = state[(long long)r * kStateWordsTc + LEIDA_KM_ST_ACTIVE] != 0 ? run_k[r] : 0;
+        const int c = K > 0 ? read_width(K) >> 2 : 0;
+        s_k[r] = (short)K;
+        s_cls[r] = (unsigned char)c;
+        if (c) atomicAdd(&s_cnt[c], 1);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int cnt[PLAN_CLASSES], target[PLAN_CLASSES], stay[PLAN_CLASSES], cur_tile[PLAN_CLASSES], cur_n[PLAN_CLASSES];
-        for (int c = 0; c < PLAN_CLASSES; ++c) { cnt[c] = 0; target[c] = 0; cur_tile[c] = -1; cur_n[c] = 0; }
         int np = 0;
-        for (int r = 0; r < n_runs; ++r)
-            if (s_k[r] > 0) { ++cnt[read_width(s_k[r]) >> 2]; ++np; }
+        for (int c = 0; c < PLAN_CLASSES; ++c) { cnt[c] = s_cnt[c]; np += cnt[c]; target[c] = 0; cur_tile[c] = -1; cur_n[c] = 0; }
+        // Runs of one width class come in long stretches (the sweep is K-major), so the state of the current class
+        // lives in registers and the per-class arrays (local memory: dynamic indexing) are touched only on a change.
         // ascending: the remainder of class c moves to the narrowest wider class whose part-filled tile can take it
         for (int c = 1; c < PLAN_CLASSES; ++c) {
             const int cap = BN / (4 * c), rem = cnt[c] % cap;
@@ -412,26 +423,39 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
         }
         for (int c = 0; c < PLAN_CLASSES; ++c) stay[c] = cnt[c];
         int n_tiles = 0;
+        int cc = -1, c_stay = 0, c_tile = -1, c_n = 0, c_cap = 1, c_w = 4;
+        auto flush = [&]() {
+            if (cc >= 0) {
+                stay[cc] = c_stay; cur_tile[cc] = c_tile; cur_n[cc] = c_n;
+                if (c_tile >= 0) s_tcount[c_tile] = (short)c_n;
+            }
+        };
+        auto load = [&](int c) {
+            cc = c; c_stay = stay[c]; c_tile = cur_tile[c]; c_n = cur_n[c]; c_w = 4 * c; c_cap = BN / c_w;
+        };
         for (int r = 0; r < n_runs; ++r) {
-            const int K = s_k[r];
+            const int c = s_cls[r];
             int v = -1;
-            if (K > 0) {
-                int c = read_width(K) >> 2;
-                while (stay[c] == 0 && target[c] != 0) c = target[c];   // arrivals beyond the class's share move on
-                --stay[c];
-                const int w = 4 * c;
-                if (cur_tile[c] < 0 || cur_n[c] == BN / w) {
-                    cur_tile[c] = n_tiles++;
-                    cur_n[c] = 0;
-                    s_tw[cur_tile[c]] = (unsigned char)w;
-                    s_tcount[cur_tile[c]] = 0;
+            if (c) {
+                if (c != cc) { flush(); load(c); }
+                while (c_stay == 0 && target[cc] != 0) {           // arrivals beyond the class's share move on
+                    const int d = target[cc];
+                    flush();
+                    load(d);
                 }
-                v = (cur_tile[c] * BN + cur_n[c] * w) | (w << 24);
-                ++cur_n[c];
-                ++s_tcount[cur_tile[c]];
+                --c_stay;
+                if (c_tile < 0 || c_n == c_cap) {
+                    if (c_tile >= 0) s_tcount[c_tile] = (short)c_n;
+                    c_tile = n_tiles++;
+                    c_n = 0;
+                    s_tw[c_tile] = (unsigned char)c_w;
+                }
+                v = (c_tile * BN + c_n * c_w) | (c_w << 24);
+                ++c_n;
             }
             s_pc[r] = v;
         }
+        flush();
         int first = 0;
         for (int t = 0; t < n_tiles; ++t) { s_tfirst[t] = (short)first; first += s_tcount[t]; }
         s_tiles = n_tiles;
