@@ -27,7 +27,8 @@ constexpr int STAGE_BYTES = 4 * BM * BK * 2;          // X1, X2, C1, C2 blocks: 
 constexpr int EPI_SPLIT = 4;                          // epilogue warps per TMEM lane quarter
 constexpr int EPI_WARPS = 4 * EPI_SPLIT;
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int TMEM_COLS = 256;                        // two fp32 accumulators of BN columns
+constexpr int N_ACC = 4;                              // fp32 accumulators of BN columns in flight (all 512 TMEM columns)
+constexpr int TMEM_COLS = N_ACC * BN;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -240,14 +241,14 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + ST * STAGE_BYTES);
     uint64_t* full = bars;            // [ST]
     uint64_t* empty = bars + ST;      // [ST]
-    uint64_t* tfull = bars + 2 * ST;  // [2]
-    uint64_t* tempty = tfull + 2;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tfull = bars + 2 * ST;      // [N_ACC]
+    uint64_t* tempty = tfull + N_ACC;     // [N_ACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + N_ACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * EPI_WARPS); }
+        for (int a = 0; a < N_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -303,8 +304,7 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
                         if (++stage == ST) { stage = 0; phase ^= 1; }
                     }
                     tc_commit(&tfull[acc]);
-                    acc ^= 1;
-                    if (acc == 0) aphase ^= 1;
+                    if (++acc == N_ACC) { acc = 0; aphase ^= 1; }
                 }
         }
     } else if (n_ct > 0) {
@@ -339,8 +339,7 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);            // accumulator may be overwritten by the next tile
-                acc ^= 1;
-                if (acc == 0) aphase ^= 1;
+                if (++acc == N_ACC) { acc = 0; aphase ^= 1; }
             }
         }
     }
