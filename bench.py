@@ -388,6 +388,8 @@ def native_arm(args):
                        "lockstep_passes_per_step": stats["lockstep"],
                        "fp64_rechecks_per_step": stats["rechecked"], "label_changes_per_step": stats["changed"],
                        "init": "explicit init rows from default_rng(0), shared with the CPU arm",
+                       "e2e_call": "Leida.from_arrays(ts, classes).fit_predict(..., scores=False, stats=False): the metric is "
+                                   "phase->eigvec->k-means->metrics (SURVEY 8d); quality scores and permutation tests are separate stages",
                        "l2_flush_between_steps": True, "per_step_ms": [round(v, 2) for v in per_step_ms], "parallelism": f"subjects sharded over {world} GPU(s)"},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": h2d * world,
