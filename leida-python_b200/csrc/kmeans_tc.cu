@@ -117,7 +117,14 @@ __host__ __device__ __forceinline__ int read_width(int K) { return tc_read_width
 // k_split_rows / pack), so no per-column masking is needed.  The cluster index is packed into the 6 low
 // mantissa bits of each score (a 2^-17 relative perturbation, covered by the error bound), which makes
 // every key unique.  (best, second) are computed together in one tree of pair merges:
-//   (m1,s1) + (m2,s2) -> (max(m1,m2), max(min(m1,m2), s1, s2))        2.5 W min/max operations in all.
+//   (m1,s1) + (m2,s2) -> (max(m1,m2), max3(min(m1,m2), s1, s2))       ~2.2 W min/max operations in all.
+// three-input maximum: one FMNMX3 on sm_100
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 template <int W>
 __device__ __forceinline__ void top2_regs(const uint32_t* r, float& best, float& second, int& bk) {
     constexpr int P = W / 2;
@@ -135,7 +142,7 @@ __device__ __forceinline__ void top2_regs(const uint32_t* r, float& best, float&
         for (int k = 0; k + o < P; k += 2 * o) {
             const float lo = fminf(m[k], m[k + o]);
             m[k] = fmaxf(m[k], m[k + o]);
-            s2[k] = fmaxf(lo, fmaxf(s2[k], s2[k + o]));
+            s2[k] = fmax3(lo, s2[k], s2[k + o]);
         }
     bk = (int)(__float_as_uint(m[0]) & 63u);
     best = __uint_as_float(__float_as_uint(m[0]) & 0xFFFFFFC0u);
