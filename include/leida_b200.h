@@ -199,13 +199,10 @@ int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int32_t* run_cr
 /* pack != 0 also writes C1/C2 from cent/cnorm (needed once after leida_kmeans_init; afterwards
  * leida_kmeans_update keeps them current).  The plan may be refreshed at any pass boundary (before
  * leida_kmeans_update); runs that stopped simply stay packed until the next refresh. */
-int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64_t x_pitch, const double* xnorm,
-                           int64_t M, int N, const void* C1, const void* C2, int64_t c_rows,
-                           const float* cent, const double* cnorm,
-                           const int32_t* plan, const int32_t* tile_first, const int32_t* tile_count,
-                           const int32_t* prun, const int32_t* pcol, const int32_t* run_k, const int32_t* run_crow0,
-                           int32_t* labels_new, int64_t* state, int32_t* worklist, int64_t worklist_cap,
-                           leida_stream_t stream);
+int leida_kmeans_tc_assign(const void* X1, const void* X2, const double* xnorm, int64_t M, int N,
+                           const void* C1, const void* C2, int64_t c_rows,
+                           const int32_t* plan, const int32_t* tile_first, const int32_t* tile_count, const int32_t* prun,
+                           int32_t* labels_new, int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
 int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int unit_rows, int n_runs_bound,
                           const int32_t* plan, const int32_t* prun,
                           const int32_t* run_k, const int32_t* run_crow0,

@@ -5,7 +5,7 @@
 // evaluated for every run at once).  fp32 operands are split into bf16 pairs (v = v1 + v2 + r,
 // |r| <= 2^-18 |v|) and the product is accumulated as X1*C1 + X1*C2 + X2*C1 in fp32 in TMEM, which
 // reproduces the fp32 product to ~2^-16 relative; the epilogue takes the top-2 scores per (row, run),
-// trusts the argmax only when the margin exceeds a rigorous error bound and queues the other rows for
+// trusts the argmax only when the margin exceeds a conservative error bound (see leida_kmeans_tc_assign; the tensor core's internal fp32 accumulation is modelled, not documented) and queues the other rows for
 // the fp64 re-check (leida_kmeans_recheck), so labels are still the fp64 argmin of the reference.
 //
 // CTA = 18 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..17 epilogue
@@ -161,7 +161,8 @@ __device__ __forceinline__ void reg_fence(uint32_t* r) {
 //   plan[0] = number of column tiles, plan[1] = number of packed (active) runs
 //   tile_first[t] & 0xffff, tile_count[t] : slice of the packed run list that lives in tile t;
 //   tile_first[t] >> 16 = TMEM read width of the tile's widest run
-//   prun[i] = run id, pcol[i] = (first column of the run inside its tile) | (K << 8)
+//   prun[i] = run id (the runs of tile t sit at columns 0, W, 2W, ... in this order);
+//   pcol[i] = (first column of the run inside its tile) | (K << 8) is written by k_plan for callers, not read here
 struct TcParams {
     long long M;
     int nkb;   // k-blocks = NPK / 64
@@ -169,8 +170,6 @@ struct TcParams {
     const int32_t* tile_first;
     const int32_t* tile_count;
     const int32_t* prun;
-    const int32_t* pcol;
-    const int32_t* run_k;
     const double* xnorm;
     float tau;
     int32_t* labels_new;
@@ -755,16 +754,13 @@ extern "C" int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int3
     return check_launch("leida_kmeans_tc_plan", pack ? 2 : 1);
 }
 
-extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const float* X, int64_t x_pitch,
-                                      const double* xnorm, int64_t M, int N, const void* C1, const void* C2,
-                                      int64_t c_rows, const float* cent, const double* cnorm, const int32_t* plan,
-                                      const int32_t* tile_first, const int32_t* tile_count, const int32_t* prun,
-                                      const int32_t* pcol, const int32_t* run_k, const int32_t* run_crow0,
-                                      int32_t* labels_new, int64_t* state, int32_t* worklist, int64_t worklist_cap,
-                                      leida_stream_t stream) {
+extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const double* xnorm, int64_t M, int N, const void* C1,
+                                      const void* C2, int64_t c_rows, const int32_t* plan, const int32_t* tile_first,
+                                      const int32_t* tile_count, const int32_t* prun, int32_t* labels_new,
+                                      int32_t* worklist, int64_t worklist_cap, leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    LEIDA_REQUIRE(X1 && X2 && X && xnorm && C1 && C2 && cent && cnorm && plan && tile_first && tile_count && prun && pcol &&
-                      run_k && run_crow0 && labels_new && state && worklist, "null pointer");
+    LEIDA_REQUIRE(X1 && X2 && xnorm && C1 && C2 && plan && tile_first && tile_count && prun && labels_new && worklist,
+                  "null pointer");
     LEIDA_REQUIRE(M >= 1 && M < (1LL << 31) && N >= 1 && c_rows >= BN, "sizes");
     const int NPK = (int)leida_kmeans_tc_pitch(N);
     CUtensorMap mx1, mx2, mc1, mc2;
@@ -774,7 +770,7 @@ extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const floa
         return rc;
     TcParams p;
     p.M = M; p.nkb = NPK / BK; p.plan = plan; p.tile_first = tile_first; p.tile_count = tile_count;
-    p.prun = prun; p.pcol = pcol; p.run_k = run_k; p.xnorm = xnorm;
+    p.prun = prun; p.xnorm = xnorm;
     // Error bound of a score, in units of |x| (the centroids are unit vectors, so sum|x_j c_j| <= |x|):
     //   dropped split terms x2*c2, x*rc, rx*c                       3 * 2^-18
     //   fp32 normalisation of the centroid                           2^-22

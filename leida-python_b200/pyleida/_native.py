@@ -48,8 +48,7 @@ SIGNATURES = {
     "leida_kmeans_tc_pitch": (c_int64, [c_int]),
     "leida_kmeans_tc_split_rows": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P]),
     "leida_kmeans_tc_plan": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
-    "leida_kmeans_tc_assign": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P,
-                                       _P, _P, _P, _P, _P, c_int64, _P]),
+    "leida_kmeans_tc_assign": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "leida_kmeans_tc_apply": (c_int, [_P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_update": (c_int, [c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_update_peers": (c_int, [c_int, _P, _P, c_int, c_int64, _P, c_int, c_int64, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),

@@ -212,10 +212,9 @@ class KMeansEngine:
                 f = fast.get(("assign", stq))
                 if f is None:
                     f = fast[("assign", stq)] = nv.prepared(
-                        "leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.X), self.XP, nv.ptr(self.xnorm), self.M,
-                        self.N, nv.ptr(c1), nv.ptr(c2), c_rows, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(plan), nv.ptr(tile_first),
-                        nv.ptr(tile_count), nv.ptr(prun), nv.ptr(pcol), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels_new),
-                        nv.ptr(state), nv.ptr(worklist), cap, stq)
+                        "leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.xnorm), self.M, self.N, nv.ptr(c1), nv.ptr(c2),
+                        c_rows, nv.ptr(plan), nv.ptr(tile_first), nv.ptr(tile_count), nv.ptr(prun), nv.ptr(labels_new),
+                        nv.ptr(worklist), cap, stq)
                 f()
                 return
             for (a, b, kmax) in groups:
