@@ -267,6 +267,10 @@ int leida_kmeans_transform_f64(const float* X, int64_t M, int N, int64_t x_pitch
 /* labels[i] = lut[labels[i]]  (KMeansLeida._remap_labels, clustering/_clustering.py:234-247;
  * the permutation itself is computed on the host with the reference's numpy calls). */
 int leida_remap_labels_i32(int32_t* labels, int64_t M, const int32_t* lut, int K, leida_stream_t stream);
+/* The same for the selected run of every K at once: out[c][i] = lut[c * kmax + labels[src_run[c]][i]], labels being the
+ * (n_runs, M) label array of the sweep and src_run[c] the row of the best restart of the c-th K (:139-146). */
+int leida_remap_labels_batch_i32(const int32_t* labels, int64_t M, int n_out, const int32_t* src_run,
+                                 const int32_t* lut, int kmax, int32_t* out, leida_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Clustering quality scores of identify_states (clustering/_clustering.py:331-339, dunn_fast :934-973;

@@ -746,6 +746,18 @@ __global__ void k_remap(int32_t* labels, long long M, const int32_t* __restrict_
     }
 }
 
+// out[c][i] = lut[c][labels[src_run[c]][i]] for every selected run c: the relabelled labels of the best restart
+// of every K in one launch.  grid = (ceil(M / 256), n_out).
+__global__ void k_remap_batch(const int32_t* __restrict__ labels, long long M, const int32_t* __restrict__ src_run,
+                              const int32_t* __restrict__ lut, int kmax, int32_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (i < M) {
+        const int l = labels[(long long)src_run[c] * M + i];
+        out[(long long)c * M + i] = (l >= 0 && l < kmax) ? lut[c * kmax + l] : l;
+    }
+}
+
 template <int KP, int RPT>
 static int launch_assign(const AssignParams& p, int n_runs, cudaStream_t st) {
     constexpr int TR = 128 * RPT;
@@ -952,4 +964,14 @@ extern "C" int leida_remap_labels_i32(int32_t* labels, int64_t M, const int32_t*
     if (M == 0) return LEIDA_OK;
     k_remap<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, M, lut, K);
     return check_launch("k_remap");
+}
+
+extern "C" int leida_remap_labels_batch_i32(const int32_t* labels, int64_t M, int n_out, const int32_t* src_run,
+                                            const int32_t* lut, int kmax, int32_t* out, leida_stream_t stream) {
+    LEIDA_REQUIRE(labels && src_run && lut && out, "null pointer");
+    LEIDA_REQUIRE(M >= 0 && n_out >= 1 && n_out <= 65535 && kmax >= 1, "sizes");
+    if (M == 0) return LEIDA_OK;
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)n_out);
+    k_remap_batch<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, M, src_run, lut, kmax, out);
+    return check_launch("k_remap_batch");
 }

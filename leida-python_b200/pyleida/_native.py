@@ -58,6 +58,7 @@ SIGNATURES = {
     "leida_remap_labels_i32": (c_int, [_P, c_int64, _P, c_int, _P]),
     "leida_scores_cosine": (c_int, [_P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "leida_scores_db": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P]),
+    "leida_remap_labels_batch_i32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P]),
     "leida_stats_moments_f64": (c_int, [_P, c_int64, c_int, _P, c_int, _P, c_int, _P, _P]),
     "leida_perm_ttest_ind_f64": (c_int, [_P, c_int64, c_int, _P, c_int, _P, c_int, _P, c_int, _P, ctypes.c_uint64, _P, _P, _P, _P]),
     "leida_perm_paired_f64": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_int, _P, ctypes.c_uint64, _P, _P, _P, _P]),

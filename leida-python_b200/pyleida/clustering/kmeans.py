@@ -493,24 +493,17 @@ class KMeansLeida:
         first = _dedupe(inits)
         uniq = sorted(set(first))
         res = eng.run([(self._k_, inits[i]) for i in uniq], n_iter=self._n_iter_, centroid_update=centroid_update)
-        self._finish(eng, res, [uniq.index(f) for f in first])
+        fitted = select_models(eng, res, {self._k_: [uniq.index(f) for f in first]}, self._n_init_)[self._k_]
+        self.__dict__.update({k: v for k, v in fitted.__dict__.items() if k not in ("_k_", "_metric_", "_n_iter_", "_n_init_")})
         return self
 
-    def _finish(self, eng, res, run_of_init, to_host=True):
-        inertias = [res.inertia(r) for r in run_of_init]
-        best_init = _select_best(inertias)
-        r = run_of_init[best_init]
-        lut, order = _remap_permutation(res.counts(r))
-        torch = eng.torch
-        lab = res.labels_device(r).clone()
-        lut_d = torch.from_numpy(lut).to(lab.device)
-        nv.call("leida_remap_labels_i32", nv.ptr(lab), lab.numel(), nv.ptr(lut_d), len(lut), nv.stream())
-        self.labels_device_ = lab
-        self.centers_device_ = res.centers_device(r)[torch.from_numpy(np.ascontiguousarray(order)).to(lab.device)]
+    def _finish(self, eng, res, r, best_init, inertias, order, labels_device, centers_device, to_host=True):
+        self.labels_device_ = labels_device
+        self.centers_device_ = centers_device
         self._centers_exact = lambda: res.centers_exact(r)[order, :]
         if to_host:
-            self.labels_ = lab.cpu().numpy().astype(np.int64)
-            self.cluster_centers_ = self.centers_device_.cpu().numpy()
+            self.labels_ = labels_device.cpu().numpy().astype(np.int64)
+            self.cluster_centers_ = centers_device.cpu().numpy()
         self.inertia_ = np.float64(inertias[best_init])
         self.n_passes_ = res.passes(r)
         self.inertia_runs_ = inertias
@@ -577,14 +570,47 @@ def sweep_runs(M, K_min, K_max, n_init, random_state=None, init_indices=None):
     return runs, plan
 
 
-def select_models(engine, res, plan, n_init, to_host=True):
-    """Best restart per K (:139-146) + relabelling (:234-247) -> {k: fitted KMeansLeida}."""
-    models = {}
-    for k, run_of_init in plan.items():
+def select_models(engine, res, plan, n_init, to_host=True, stacked=False):
+    """Best restart per K (:139-146) + relabelling (:234-247) -> {k: fitted KMeansLeida}.  The choices are host
+    decisions on a few numbers per run; the device work -- relabelling the chosen run of every K and picking its
+    centroid rows -- is one upload and one launch for all K.  stacked=True also returns the (n_K, M) int32 device
+    array of all relabelled label rows (K in plan order)."""
+    torch = engine.torch
+    ks = list(plan.keys())
+    picks = []
+    for k in ks:
+        inertias = [res.inertia(r) for r in plan[k]]
+        best_init = _select_best(inertias)
+        r = plan[k][best_init]
+        lut, order = _remap_permutation(res.counts(r))
+        picks.append((k, r, best_init, inertias, lut, order))
+    kmax = max(len(p[4]) for p in picks)
+    n_out = len(picks)
+    row_of = np.asarray([res._inv[p[1]] for p in picks], dtype=np.int32)
+    luts = np.zeros((n_out, kmax), dtype=np.int32)
+    crow = []
+    for c, p in enumerate(picks):
+        luts[c, :len(p[4])] = p[4]
+        j = res._inv[p[1]]
+        crow.append(int(res._crow0[j]) + np.asarray(p[5], dtype=np.int64))
+    # one pinned-free upload: [src rows | luts | centroid rows]
+    blob = np.concatenate([row_of.astype(np.int64), luts.reshape(-1).astype(np.int64), np.concatenate(crow)])
+    d_blob = torch.from_numpy(blob).to(res._labels.device)
+    d_rows = d_blob[:n_out].to(torch.int32)
+    d_luts = d_blob[n_out:n_out + n_out * kmax].to(torch.int32)
+    d_crow = d_blob[n_out + n_out * kmax:]
+    M = int(res._labels.shape[1])
+    labels_all = torch.empty((n_out, M), dtype=torch.int32, device=res._labels.device)
+    nv.call("leida_remap_labels_batch_i32", nv.ptr(res._labels), M, n_out, nv.ptr(d_rows), nv.ptr(d_luts), kmax,
+            nv.ptr(labels_all), nv.stream())
+    centers_all = res._cent[d_crow][:, :engine.N]                   # (sum K, N) in the relabelled order
+    models, off = {}, 0
+    for c, (k, r, best_init, inertias, lut, order) in enumerate(picks):
         km = KMeansLeida(k=k, n_init=n_init, n_iter=1_000)
-        km._finish(engine, res, run_of_init, to_host=to_host)
+        km._finish(engine, res, r, best_init, inertias, order, labels_all[c], centers_all[off:off + len(order)], to_host)
+        off += len(order)
         models[k] = km
-    return models
+    return (models, labels_all) if stacked else models
 
 
 def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=None, plot=True, save_results=False,

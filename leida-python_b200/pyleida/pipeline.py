@@ -47,9 +47,8 @@ def run_device(blocks, n_rois, seg_off, seg_rows, K_min=2, K_max=20, n_init=15, 
     engine = KMeansEngine(x32, n_features=N, comm=comm, row_lo=int(off[comm.rank]), m_global=int(off[-1]))
     runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices)
     batch = engine.run(runs, n_iter=1_000, centroid_update=centroid_update, profile=profile)   # stage 3 (:314-321)
-    models = select_models(engine, batch, plan, n_init, to_host=False)
+    models, labels = select_models(engine, batch, plan, n_init, to_host=False, stacked=True)   # labels: (n_cols, M) int32
     ks = list(range(K_min, K_max + 1))
-    labels = torch.stack([models[k].labels_device_ for k in ks])            # (n_cols, M) int32
     col_k = np.asarray(ks, dtype=np.int32)
     G = int(seg_off.numel()) - 1
     kmax = int(col_k.max())
