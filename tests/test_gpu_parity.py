@@ -647,3 +647,33 @@ def test_permtest_rel_and_compute_stats(P, O):
     for j, r in enumerate(mine):
         assert t["statistic"][j] == pytest.approx(r["statistic"], rel=1e-11)
         assert t["test"][j] == r["test"] and t["effect_size"][j] == pytest.approx(r["effect_size"], rel=1e-11)
+
+
+def test_stats_stage_edge_cases(P, O):
+    """One condition: the statistics stage is skipped and Leida.stats says so; argument validation follows the
+    reference (stats/_stats.py:86-92, 314-318); both randomised p-value rules differ exactly by the +1 adjustment."""
+    import pandas as pd
+    from pyleida import synthetic
+    ts, _ = synthetic.make_dataset(6, 16, 60, "states")
+    one = {s: ["A"] for s in ts}
+    m = P.Leida.from_arrays(ts, one).fit_predict(TR=1.0, K_min=2, K_max=3, n_init=1, random_state=0, scores=False)
+    with pytest.raises(Exception):
+        m.stats(2)
+    rng = np.random.default_rng(8)
+    df = pd.DataFrame(rng.normal(size=(24, 3)), columns=["a", "b", "c"])
+    df.insert(0, "condition", ["x"] * 11 + ["y"] * 13)
+    with pytest.raises(ValueError):
+        P.stats.permtest_ind(df, class_column=None)
+    with pytest.raises(ValueError):
+        P.stats.permtest_ind(df, class_column="group")
+    with pytest.raises(TypeError):
+        P.stats.permtest_ind(df, class_column="condition", n_perm=100.0)
+    with pytest.raises(ValueError):
+        P.stats._compute_stats({"occupancies": {"k_2": df}, "dwell_times": {"k_2": df}}, alternative="both", save_results=False)
+    with pytest.raises(ValueError):
+        P.stats.permtest_rel(df, class_column="condition")                       # 11 vs 13 rows cannot be paired
+    a = P.stats.permtest_ind(df, class_column="condition", n_perm=999, random_state=3)
+    b = P.stats.permtest_ind(df, class_column="condition", n_perm=999, random_state=3, adjustment="none")
+    assert np.allclose(a["p-value"].values * 1000 - 1, b["p-value"].values * 999, atol=1e-9)
+    g = P.stats.hedges_g(df.a.values[:11], df.a.values[11:])
+    assert g == O.hedges_g(df.a.values[:11], df.a.values[11:]) and a["effect_size"][0] == pytest.approx(g, rel=1e-12)
