@@ -1,4 +1,4 @@
-"""Times the first lock-step assign pass (all 285 runs active) of the config-1 sweep; used with debug knobs."""
+"""Times the first lock-step assign passes (all 285 runs active) of the config-1 sweep."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "leida-python_b200"))
@@ -19,7 +19,7 @@ for rep in range(2):
     try:
         res = eng.run(runs, n_iter=12, profile=prof)
     except Exception as e:
-        print("run failed (expected with debug knobs):", type(e).__name__)
+        print("run failed:", type(e).__name__)
     torch.cuda.synchronize()
     a = [e0.elapsed_time(e1) for e0, e1 in prof["assign"]]
     print("assign first %.3f  p2 %.3f p5 %.3f p10 %.3f" % tuple(a[i] if i < len(a) else -1 for i in (0, 2, 5, 10)))
