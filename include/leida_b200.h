@@ -234,10 +234,11 @@ int leida_kmeans_update_peers(int n_runs, const int32_t* run_k, const int32_t* r
                               int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
                               int32_t* mailbox, leida_stream_t stream);
 /* n_active_out: device int32[8], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
- * [2] = runs still active after this call, [3] = calls completed, [4] = first all-stopped call).  mailbox (may be NULL): HOST-visible (pinned, mapped)
- * int32[4]; the last CTA stores {runs still active, number of update calls completed, index of the
- * first update call that left no run active (0 = not yet)} there so the host can follow convergence
- * without synchronising or copying.  With several ranks the values are identical on every rank (they
+ * [2] = runs still active after this call, [3] = calls completed, [4] = first all-stopped call).  mailbox (may be NULL): HOST-visible (pinned, mapped),
+ * 8-byte aligned; the last CTA publishes ONE 64-bit word there -- bits 0-15 runs still active, bits 16-39 number
+ * of update calls completed, bits 40-63 index of the first update call that left no run active (0 = not yet) --
+ * so the host can follow convergence without synchronising or copying (n_runs <= 65535, calls < 2^24).
+ * With several ranks the values are identical on every rank (they
  * derive from all-reduced counters), which lets all ranks issue the same number of passes. */
 /* run_pcol / C1 / C2 (all NULL in the SIMT flow): the tensor-core operands of every packed run --
  * unit-normalised centroids split into bf16 hi/lo rows at the run's packed column -- are rewritten

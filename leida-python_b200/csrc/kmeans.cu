@@ -507,14 +507,15 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             n_active[1] = 0;
             if (mailbox) {
                 // device-side copy of the counters (n_active[3] = passes done, n_active[4] = first all-stopped
-                // pass), published to the host with two plain stores ordered by one system fence
+                // pass), published to the host as ONE aligned 64-bit store -- a single PCIe write, so the three
+                // fields are always consistent and no system fence sits on the kernel's tail:
+                //   bits 0-15 active runs | bits 16-39 passes done | bits 40-63 first all-stopped pass (0 = not yet)
                 const int done = n_active[3] + 1;
                 n_active[3] = done;
                 if (na == 0 && n_active[4] == 0) n_active[4] = done;
-                mailbox[0] = na;
-                mailbox[2] = n_active[4];
-                __threadfence_system();
-                mailbox[1] = done;
+                const unsigned long long word = (unsigned long long)(na & 0xFFFF) | ((unsigned long long)(done & 0xFFFFFF) << 16) |
+                                                ((unsigned long long)(n_active[4] & 0xFFFFFF) << 40);
+                *reinterpret_cast<volatile unsigned long long*>(mailbox) = word;
             }
         }
     }

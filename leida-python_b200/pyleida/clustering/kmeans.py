@@ -142,7 +142,11 @@ class KMeansEngine:
         worklist[:8].zero_()
         n_active = torch.zeros(8, dtype=torch.int32, device=dev)
         mailbox = torch.zeros(4, dtype=torch.int32, pin_memory=True)   # written by the last CTA of leida_kmeans_update
-        mb = mailbox.numpy()
+        mb64 = mailbox.numpy().view(np.int64)          # one packed word: active | passes done << 16 | first stop << 40
+
+        def mb_read():
+            v = int(mb64[0])
+            return v & 0xFFFF, (v >> 16) & 0xFFFFFF, (v >> 40) & 0xFFFFFF
         st = nv.stream()
 
         peers = None
@@ -282,14 +286,14 @@ class KMeansEngine:
         time_assign = profile is not None and (profile.get("*") or "assign" in profile)
         eager_rest = profile is not None and any(k in profile for k in ("*", "recheck", "apply", "update"))
         max_lag = 6
-        mb[:] = 0
+        mb64[:] = 0
         packed_bound = R
         active_bound = R
         grid_bound = [R]        # upper bound of the packed-run count, sizes the apply grid (eager launches only)
         issued = 0
         graphs = None
         while True:
-            if tc and mb[2] == 0 and 0 < active_bound <= 0.9 * packed_bound:
+            if tc and mb_read()[2] == 0 and 0 < active_bound <= 0.9 * packed_bound:
                 tc_plan()                              # re-pack: only the runs still active keep tensor-core columns
                 packed_bound = active_bound
                 if not use_graph:
@@ -307,15 +311,16 @@ class KMeansEngine:
             else:
                 graphs[0].replay()
             issued += 1
-            while issued - int(mb[1]) > max_lag:
+            while issued - mb_read()[1] > max_lag:
                 pass
-            if mb[1] >= 1:
-                active_bound = min(active_bound, int(mb[0]))
+            n_act, n_done, first_stop = mb_read()          # one word: the three fields belong to the same pass
+            if n_done >= 1:
+                active_bound = min(active_bound, n_act)
             # Stop rule, identical on every rank (the collectives inside the passes must match): the
             # device records the pass p0 after which no run was active; because the host checks after
             # every issue and is never more than max_lag passes ahead, issued <= p0 + max_lag when p0
             # becomes visible, and every rank issues exactly p0 + max_lag passes.
-            if mb[2] > 0 and issued >= int(mb[2]) + max_lag:
+            if first_stop > 0 and issued >= first_stop + max_lag:
                 break
             if issued > n_iter + 2 + 2 * max_lag:
                 raise nv.LeidaCudaError("k-means did not terminate (internal error)")
