@@ -126,6 +126,8 @@ int    leida_eigvec_dense_f64(const double* dfc, int N, int n_vol, double* out, 
 #define LEIDA_KM_ST_K          7   /* K of the run (set by leida_kmeans_init)                     */
 #define LEIDA_KM_ST_RECHECK_TOTAL 8  /* rows re-evaluated in fp64 over all passes (global count)    */
 #define LEIDA_KM_ST_CHANGED_TOTAL 9  /* label changes over all passes (global count)                */
+#define LEIDA_KM_ST_TAU_WATCH  10  /* float bits: largest tensor-core margin, as a fraction of the trust threshold, at
+                                      which the fp64 re-check overruled the tensor-core argmax (0 = never); local     */
 
 #define LEIDA_KM_MAX_K         64
 
@@ -149,18 +151,22 @@ int leida_kmeans_init(const float* X_init, int64_t xi_pitch, const int64_t* init
  * row whose top-2 margin is inside the fp32 error bound, so labels equal the fp64 argmin.  Rows
  * whose label changed move their fixed-point contribution between clusters in `acc`.
  * kmax (host value) = max K over the runs of this call; it selects the register tile, so callers
- * group runs of similar K.  worklist: device int32 (2*worklist_cap + 8), header zeroed once by the
- * caller: rows the fp32 pass cannot decide are queued there (rows that do not fit are resolved
- * inline, slower but identical) and MUST be resolved by leida_kmeans_recheck on the same stream
- * before the next leida_kmeans_assign / leida_kmeans_update. */
+ * group runs of similar K.  worklist: device int32 (8*worklist_cap + 8), 16-byte aligned, header (8 words)
+ * zeroed once by the caller: rows the fp32 pass cannot decide are queued there as 8-word entries
+ * {run, row, fast argmax or -1, margin / threshold (float bits), candidate mask lo, hi, 0, 0} (rows that do
+ * not fit are resolved inline, slower but identical) and MUST be resolved by leida_kmeans_recheck on the
+ * same stream before the next leida_kmeans_assign / leida_kmeans_update. */
 int leida_kmeans_assign(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                         int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
                         const float* cent, const double* cnorm, int64_t* acc,
                         int32_t* labels, int64_t* state,
                         int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
 
-/* fp64 re-evaluation of the queued rows with the reference's arithmetic order (scipy cdist
- * 'cosine': sequential dot, dot/(|u||v|), clip, 1-cos; first minimum); empties the queue. */
+/* fp64 re-evaluation of the queued rows with the reference's arithmetic (scipy cdist 'cosine':
+ * dot/(|u||v|), clip, 1-cos; first minimum) over the entry's candidate clusters (empty mask = all K: the
+ * candidates are the clusters whose fast score was within the trust threshold of the best, which always
+ * include the fp64 argmin); empties the queue.  When the fp64 argmin differs from the entry's fast argmax the
+ * entry's margin fraction is max-ed into state[LEIDA_KM_ST_TAU_WATCH]. */
 int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                          int n_runs, const int32_t* run_k, const int32_t* run_crow0,
                          const float* cent, const double* cnorm, int64_t* acc,
@@ -202,7 +208,19 @@ int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int32_t* run_cr
 int leida_kmeans_tc_assign(const void* X1, const void* X2, const double* xnorm, int64_t M, int N,
                            const void* C1, const void* C2, int64_t c_rows,
                            const int32_t* plan, const int32_t* tile_first, const int32_t* tile_count, const int32_t* prun,
-                           int32_t* labels_new, int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
+                           int32_t* labels_new, int32_t* worklist, int64_t worklist_cap, double tau,
+                           leida_stream_t stream);
+/* tau: trust threshold on (best - second) / |x|; <= 0 selects leida_kmeans_tc_tau(N), the measured error bound
+ * of the bf16 x 3 tensor-core score (kmeans_tc.cu: default_tau). */
+double leida_kmeans_tc_tau(int N);
+/* Same launch, additionally storing the raw fp32 tensor-core scores: scores (M, score_pitch >= c_rows), column =
+ * packed centroid column (run_pcol).  Verification entry: the tests compare the scores with fp64 to measure the
+ * error bound that leida_kmeans_tc_tau encodes. */
+int leida_kmeans_tc_scores(const void* X1, const void* X2, const double* xnorm, int64_t M, int N,
+                           const void* C1, const void* C2, int64_t c_rows,
+                           const int32_t* plan, const int32_t* tile_first, const int32_t* tile_count, const int32_t* prun,
+                           int32_t* labels_new, int32_t* worklist, int64_t worklist_cap,
+                           float* scores, int64_t score_pitch, leida_stream_t stream);
 int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int unit_rows, int n_runs_bound,
                           const int32_t* plan, const int32_t* prun,
                           const int32_t* run_k, const int32_t* run_crow0,

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
+#include <type_traits>
 
 namespace leida {
 
@@ -191,8 +192,9 @@ __global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
         } else {
             const int slot = atomicAdd(p.worklist, 1);
             if (slot < p.worklist_cap) {
-                p.worklist[8 + 2 * (long long)slot] = run;
-                p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
+                int4* e = reinterpret_cast<int4*>(p.worklist + 8) + 2 * (long long)slot;
+                e[0] = make_int4(run, (int32_t)row, -1, 0);       // no tensor-core argmax to compare with
+                e[1] = make_int4(0, 0, 0, 0);                      // empty candidate mask = all K clusters
             } else {
                 // work list full: resolve here, serially (slow, correct)
                 const float* xr = p.X + row * p.XP;
@@ -227,12 +229,13 @@ __global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
     if (tid == 0 && nchg > 0) atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_CHANGED, nchg);
 }
 
-// fp64 re-evaluation of the rows the fast pass could not decide.  One warp per (run,row) entry:
-// the row is held in registers as doubles (lanes stride the columns), every centroid's dot product
-// is an fp64 FMA chain per lane plus a fixed-order butterfly sum, then the reference's formula
-// 1 - dot/(|x||c|) with clipping, first minimum wins.  (scipy's own build sums the dot product in two
-// SIMD lanes, so no particular fp64 summation order is "the" reference; any fp64 order agrees with it
-// to ~1e-16 and decides identically unless two distances coincide to that level.)
+// fp64 re-evaluation of the rows the fast pass could not decide.  One warp per queue entry
+// {run, row, fast argmax, margin/threshold, candidate mask (64 bits), -, -}: the row is held in registers as
+// doubles (lanes stride the columns), the dot product with every CANDIDATE centroid (the clusters whose fast score
+// was within the threshold of the best; empty mask = all K) is an fp64 FMA chain per lane plus a fixed-order
+// butterfly sum, then the reference's formula 1 - dot/(|x||c|) with clipping, first minimum wins.  (scipy's own
+// build sums the dot product in two SIMD lanes, so no particular fp64 summation order is "the" reference; any fp64
+// order agrees with it to ~1e-16 and decides identically unless two distances coincide to that level.)
 // CPL = columns per lane held in registers (rows up to 32*CPL columns); CPL = 0: rows stay in memory.
 template <int CPL>
 __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
@@ -243,9 +246,12 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
     const long long queued = p.worklist[0];
     const long long count = queued > p.worklist_cap ? p.worklist_cap : queued;
     constexpr bool in_regs = CPL > 0;
-    auto resolve = [&](int run, long long row) {
+    auto resolve = [&](int run, long long row, unsigned long long mask, int fast_k, int ratio_bits) {
         const int K = p.run_k[run];
         const int crow0 = p.run_crow0[run];
+        const unsigned long long all = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
+        mask &= all;
+        if (mask == 0) mask = all;
         const float* xr = p.X + row * p.XP;
         const double xn = p.xnorm[row];
         double xv[RECHECK_MAX_COLS_PER_LANE];
@@ -259,13 +265,25 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
         double bd = INFINITY;
         int bk = 0;
         bool any_nan = false;
-        for (int k0 = 0; k0 < K; k0 += 4) {
-            double s4[4] = {0.0, 0.0, 0.0, 0.0};
-            if (in_regs) {
-                float cv[4][RECHECK_MAX_COLS_PER_LANE];
+        // candidates in increasing k (first minimum wins), U at a time: two when that covers the mask (the usual
+        // case: best and second), else four
+        auto batch = [&](auto tag) {
+            constexpr int U = decltype(tag)::value;
+            int ks[U];
+            int n = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float* cr = p.cent + (long long)(crow0 + min(k0 + u, K - 1)) * p.XP;
+            for (int u = 0; u < U; ++u) {
+                if (mask) { ks[u] = __ffsll((long long)mask) - 1; mask &= mask - 1; n = u + 1; }
+                else ks[u] = ks[u > 0 ? u - 1 : 0];
+            }
+            double s[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] = 0.0;
+            if (in_regs) {
+                float cv[U][RECHECK_MAX_COLS_PER_LANE];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float* cr = p.cent + (long long)(crow0 + ks[u]) * p.XP;
 #pragma unroll
                     for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) {
                         const int j = lane + 32 * i;
@@ -273,31 +291,38 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) s4[u] = fma(xv[i], (double)cv[u][i], s4[u]);
+                    for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) s[u] = fma(xv[i], (double)cv[u][i], s[u]);
             } else {
-                for (int u = 0; u < 4; ++u) {
-                    const float* cr = p.cent + (long long)(crow0 + min(k0 + u, K - 1)) * p.XP;
-                    for (int j = lane; j < p.N; j += 32) s4[u] = fma((double)xr[j], (double)cr[j], s4[u]);
+                for (int u = 0; u < U; ++u) {
+                    const float* cr = p.cent + (long long)(crow0 + ks[u]) * p.XP;
+                    for (int j = lane; j < p.N; j += 32) s[u] = fma((double)xr[j], (double)cr[j], s[u]);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) s4[u] = warp_sum(s4[u]);
+            for (int u = 0; u < U; ++u) s[u] = warp_sum(s[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = k0 + u;
-                if (k < K) {
-                    const double d = cosine_distance(s4[u], xn, p.cnorm[crow0 + k]);
+            for (int u = 0; u < U; ++u) {
+                if (u < n) {
+                    const int k = ks[u];
+                    const double d = cosine_distance(s[u], xn, p.cnorm[crow0 + k]);
                     if (d != d && !any_nan) { any_nan = true; bd = -INFINITY; bk = k; }   // numpy argmin: first NaN wins
                     if (d < bd) { bd = d; bk = k; }
                 }
             }
+        };
+        while (mask) {
+            if (__popcll(mask) <= 2) batch(std::integral_constant<int, 2>());
+            else batch(std::integral_constant<int, 4>());
         }
         if (p.labels_out) {
             if (lane == 0) {
                 p.labels_out[(long long)run * p.M + row] = bk;
                 atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
+                // watch on the error bound: the fast argmax lost although its margin was ratio * threshold
+                if (fast_k >= 0 && fast_k != bk)
+                    atomicMax(p.state + (long long)run * kStateWords + LEIDA_KM_ST_TAU_WATCH, (long long)ratio_bits);
             }
             return;
         }
@@ -313,11 +338,15 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
         }
         if (lane == 0) atomic_add_ll(p.state + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED, 1);
     };
-    for (long long e = warp; e < count; e += nwarps) resolve(p.worklist[8 + 2 * e], p.worklist[8 + 2 * e + 1]);
+    const int4* entries = reinterpret_cast<const int4*>(p.worklist + 8);
+    for (long long e = warp; e < count; e += nwarps) {
+        const int4 a = entries[2 * e], b = entries[2 * e + 1];
+        resolve(a.x, a.y, (unsigned long long)(uint32_t)b.x | ((unsigned long long)(uint32_t)b.y << 32), a.z, a.w);
+    }
     // Queue overflow (tensor-core flow only; its fast pass stores -2 for every undecided pair whether or
     // not the pair still fitted in the queue): find the unlisted pairs by scanning the labels of the
-    // active runs.  A pair another warp is resolving from the queue right now may be resolved twice --
-    // same inputs, same label.
+    // active runs and evaluate all K clusters for them.  A pair another warp is resolving from the queue right
+    // now may be resolved twice -- same inputs, same label.
     if (p.labels_out && queued > p.worklist_cap) {
         const long long blocks = (p.M + 31) / 32;
         for (long long b = warp; b < (long long)p.n_runs * blocks; b += nwarps) {
@@ -329,7 +358,7 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
             while (todo) {
                 const int bit = __ffs(todo) - 1;
                 todo &= todo - 1;
-                resolve(run, row0 + bit);
+                resolve(run, row0 + bit, 0ull, -1, 0);
             }
         }
     }

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <mutex>
 
 namespace leida {
 
@@ -175,6 +176,8 @@ struct TcParams {
     int32_t* labels_new;
     int32_t* worklist;
     long long worklist_cap;
+    float* dump;             // DUMP instantiation only: raw fp32 scores, (M, dump_pitch), column = packed column
+    long long dump_pitch;
 };
 
 // Columns one epilogue step reads from TMEM for a tile whose slots are W wide: a whole number of slots,
@@ -193,14 +196,24 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t t, uint32_t* r) {
     }
 }
 
+// W columns, W a multiple of 4 up to 64: largest power-of-two piece first.
+template <int W>
+__device__ __forceinline__ void tmem_ld_any(uint32_t t, uint32_t* r) {
+    if constexpr (W > 0) {
+        constexpr int A = W >= 64 ? 64 : W >= 32 ? 32 : W >= 16 ? 16 : W >= 8 ? 8 : 4;
+        tmem_ld<A>(t, r);
+        tmem_ld_any<W - A>(t + A, r + A);
+    }
+}
+
 // Epilogue of one column tile for one warp.  All slots of a tile have the same width W and sit at
 // columns 0, W, 2W, ... (k_plan), so the warp reads the tile in chunks of CH columns = CH/W runs per
 // tcgen05.ld and evaluates the runs from registers; the EPI_SPLIT warps of a lane quarter take the chunks
 // round-robin.  (Software pipelining the loads was measured and bought nothing: with this many warps the
 // scheduler already overlaps one warp's TMEM round trip with another's arithmetic.)
-template <int W>
+template <int W, bool DUMP>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int first, int cnt, int sub, int lane,
-                                              bool valid, float thr, int32_t* lab, long long row) {
+                                              bool valid, float thr, int32_t* lab, long long row, int ct) {
     constexpr int CH = chunk_cols(W), RPC = CH / W;
     const int n_chunks = (cnt + RPC - 1) / RPC;
     if (sub >= n_chunks) return;
@@ -210,6 +223,13 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr,
         tmem_ld_chunk<CH>(taddr + c * CH, r);
         tmem_ld_wait();
         reg_fence<CH>(r);
+        if constexpr (DUMP) {
+            if (valid) {
+                float* d = p.dump + row * p.dump_pitch + (long long)ct * BN + c * CH;
+#pragma unroll
+                for (int i = 0; i < CH; ++i) d[i] = __uint_as_float(r[i]);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < RPC; ++j) {
             const int i = c * RPC + j;
@@ -218,18 +238,39 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr,
                 float best, second;
                 int bk;
                 top2_regs<W>(r + j * W, best, second, bk);
-                if (valid) {
-                    int out = bk;
-                    if (!((best - second) > thr)) {
-                        // undecided at this precision: mark the pair and queue it for the fp64 re-check.  A full
-                        // queue is fine -- the re-check finds unlisted marks by scanning (k_recheck).
+                int out = bk;
+                const bool undecided = valid && !((best - second) > thr);
+                if (__any_sync(0xffffffffu, undecided)) {
+                    // Undecided at this precision (rare: a fraction of a percent of the pairs): mark the pair and queue it
+                    // for the fp64 re-check together with the set of clusters that can still be the fp64 argmin -- every
+                    // score within thr of the best (the true best's tensor-core score is at most two score errors below
+                    // the tensor-core best, and thr covers more than that) -- so the re-check evaluates 2-3 centroids,
+                    // not K.  The slot's scores are read again from TMEM (warp-collective, hence the warp-uniform branch)
+                    // instead of being kept alive in registers through the top-2 tree.  A full queue is fine: the re-check
+                    // finds unlisted marks by scanning (k_recheck) and evaluates all K for them.
+                    uint32_t q[W];
+                    tmem_ld_any<W>(taddr + c * CH + j * W, q);
+                    tmem_ld_wait();
+                    reg_fence<W>(q);
+                    if (undecided) {
                         out = -2;
+                        const float lo = best - thr;
+                        unsigned long long mask = 0;
+#pragma unroll
+                        for (int k = 0; k < W; ++k)
+                            if (__uint_as_float(q[k] & 0xFFFFFFC0u) >= lo) mask |= 1ull << k;
                         const int slot = atomicAdd(p.worklist, 1);
                         if (slot < p.worklist_cap) {
-                            p.worklist[8 + 2 * (long long)slot] = run;
-                            p.worklist[8 + 2 * (long long)slot + 1] = (int32_t)row;
+                            // margin as a fraction of the threshold: the re-check records the largest one at which the
+                            // fp64 argmin differed from the tensor-core argmax (LEIDA_KM_ST_TAU_WATCH)
+                            const float ratio = thr > 0.f ? (best - second) / thr : 0.f;
+                            int4* e = reinterpret_cast<int4*>(p.worklist + 8) + 2 * (long long)slot;
+                            e[0] = make_int4(run, (int32_t)row, bk, __float_as_int(ratio));
+                            e[1] = make_int4((int)(uint32_t)mask, (int)(uint32_t)(mask >> 32), 0, 0);
                         }
                     }
+                }
+                if (valid) {
                     lab[(long long)run * p.M] = out;
                 }
             }
@@ -237,7 +278,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr,
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool DUMP>
+__global__ void __maxnreg__(112)
 k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
             const __grid_constant__ CUtensorMap tmC1, const __grid_constant__ CUtensorMap tmC2,
             const __grid_constant__ TcParams p) {
@@ -332,16 +374,16 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
                 switch (wt) {
-                    case 4: epilogue_tile<4>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 8: epilogue_tile<8>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 12: epilogue_tile<12>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 16: epilogue_tile<16>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 20: epilogue_tile<20>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 24: epilogue_tile<24>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 32: epilogue_tile<32>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 40: epilogue_tile<40>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    case 48: epilogue_tile<48>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
-                    default: epilogue_tile<64>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row); break;
+                    case 4: epilogue_tile<4, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 8: epilogue_tile<8, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 12: epilogue_tile<12, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 16: epilogue_tile<16, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 20: epilogue_tile<20, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 24: epilogue_tile<24, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 32: epilogue_tile<32, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 40: epilogue_tile<40, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    case 48: epilogue_tile<48, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
+                    default: epilogue_tile<64, DUMP>(p, taddr, first, cnt, sub, lane, valid, thr, lab, row, ct); break;
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);            // accumulator may be overwritten by the next tile
@@ -754,45 +796,102 @@ extern "C" int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int3
     return check_launch("leida_kmeans_tc_plan", pack ? 2 : 1);
 }
 
-extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const double* xnorm, int64_t M, int N, const void* C1,
-                                      const void* C2, int64_t c_rows, const int32_t* plan, const int32_t* tile_first,
-                                      const int32_t* tile_count, const int32_t* prun, int32_t* labels_new,
-                                      int32_t* worklist, int64_t worklist_cap, leida_stream_t stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// Error bound of a tensor-core score, in units of |x| (the centroids are unit vectors, so sum|x_j c_j| <= |x|).
+//   dropped split terms x2*c2, x*rc, rx*c                        3 * 2^-18       (rigorous)
+//   fp32 normalisation of the centroid                            2^-22           (rigorous)
+//   index packing in the epilogue (6 mantissa bits)               2^-17           (rigorous)
+//   fp32 accumulation inside the tensor core over 3*NPK/16 MMAs   MEASURED, not modelled: the accumulation order and
+//   rounding of tcgen05.mma are undocumented, so leida_kmeans_tc_scores dumps the raw scores and
+//   tests/test_gpu_parity.py::test_tc_score_error compares them with fp64 (N = 116 / 400 / 1000, clustered and iid
+//   rows, ~1e8 scores each; profiles/r02_tc_score_error.txt).  acc_term below is an envelope of the observed maxima
+//   times LEIDA_TC_ACC_SAFETY.  The margin test compares two scores (x 2).
+// On top of the tests the bound is watched in production: every re-checked pair carries its tensor-core argmax and
+// margin, and LEIDA_KM_ST_TAU_WATCH records the largest margin (as a fraction of the threshold) at which the fp64
+// argmin disagreed; the host warns when that fraction exceeds 1/2.
+static float default_tau(int NPK) {
+    const float rigorous = 3.0f * 3.8147e-6f + 2.4e-7f + 7.63e-6f;
+    // PLACEHOLDER until the measurement lands: the round-1 worst-case model
+    const float acc_term = 2.0f * (3.0f * (float)(NPK / 16) * 5.0f) * 1.1921e-7f;
+    return 2.5f * (rigorous + acc_term);
+}
+
+extern "C" double leida_kmeans_tc_tau(int N) { return (double)default_tau((int)leida_kmeans_tc_pitch(N)); }
+
+namespace leida {
+// Tensor maps depend only on (device, base pointer, rows, pitch): the per-pass launches reuse them.
+struct MapKey { int dev; const void* ptr; long long rows; int npk; };
+struct MapSlot { MapKey k; CUtensorMap m; bool used; };
+static MapSlot g_maps[32];
+static int g_map_next = 0;
+static std::mutex g_map_mu;
+static bool g_attr_set[64][2];
+
+static int cached_map(CUtensorMap* out, int dev, const void* ptr, long long rows, int npk) {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    for (auto& s : g_maps)
+        if (s.used && s.k.dev == dev && s.k.ptr == ptr && s.k.rows == rows && s.k.npk == npk) { *out = s.m; return LEIDA_OK; }
+    MapSlot& s = g_maps[g_map_next];
+    g_map_next = (g_map_next + 1) % 32;
+    const int rc = make_map(&s.m, ptr, rows, npk);
+    if (rc) { s.used = false; return rc; }
+    s.k = MapKey{dev, ptr, rows, npk};
+    s.used = true;
+    *out = s.m;
+    return LEIDA_OK;
+}
+
+static int launch_tc_assign(const void* X1, const void* X2, const double* xnorm, int64_t M, int N, const void* C1,
+                            const void* C2, int64_t c_rows, const int32_t* plan, const int32_t* tile_first,
+                            const int32_t* tile_count, const int32_t* prun, int32_t* labels_new, int32_t* worklist,
+                            int64_t worklist_cap, double tau, float* dump, int64_t dump_pitch, cudaStream_t st) {
     LEIDA_REQUIRE(X1 && X2 && xnorm && C1 && C2 && plan && tile_first && tile_count && prun && labels_new && worklist,
                   "null pointer");
     LEIDA_REQUIRE(M >= 1 && M < (1LL << 31) && N >= 1 && c_rows >= BN, "sizes");
     const int NPK = (int)leida_kmeans_tc_pitch(N);
+    int dev = 0;
+    LEIDA_CUDA_TRY(cudaGetDevice(&dev));
     CUtensorMap mx1, mx2, mc1, mc2;
     int rc;
-    if ((rc = make_map(&mx1, X1, M, NPK)) || (rc = make_map(&mx2, X2, M, NPK)) || (rc = make_map(&mc1, C1, c_rows, NPK)) ||
-        (rc = make_map(&mc2, C2, c_rows, NPK)))
+    if ((rc = cached_map(&mx1, dev, X1, M, NPK)) || (rc = cached_map(&mx2, dev, X2, M, NPK)) ||
+        (rc = cached_map(&mc1, dev, C1, c_rows, NPK)) || (rc = cached_map(&mc2, dev, C2, c_rows, NPK)))
         return rc;
     TcParams p;
     p.M = M; p.nkb = NPK / BK; p.plan = plan; p.tile_first = tile_first; p.tile_count = tile_count;
     p.prun = prun; p.xnorm = xnorm;
-    // Error bound of a score, in units of |x| (the centroids are unit vectors, so sum|x_j c_j| <= |x|):
-    //   dropped split terms x2*c2, x*rc, rx*c                       3 * 2^-18
-    //   fp32 normalisation of the centroid                           2^-22
-    //   index packing in the epilogue (6 mantissa bits)              2^-17
-    //   fp32 accumulation in the tensor core: 3*NPK/16 MMAs per output, each a 16-term sum plus the add
-    //   into the accumulator -- (1 + log2 16) = 5 roundings of at most one fp32 ulp (2^-23, truncation
-    //   allowed) of a partial sum that never exceeds |x|; counted twice for safety.
-    // The margin compares two scores (x2), plus 25% slack.  tests/test_gpu_parity.py checks the bound
-    // against fp64 (labels of the tensor-core path == labels of the fp32 CUDA-core path == oracle).
-    const float acc_term = 2.0f * (3.0f * (float)(NPK / 16) * 5.0f) * 1.1921e-7f;
-    p.tau = 2.5f * (3.0f * 3.8147e-6f + 2.4e-7f + 7.63e-6f + acc_term);
+    p.tau = tau > 0.0 ? (float)tau : default_tau(NPK);
     p.labels_new = labels_new; p.worklist = worklist; p.worklist_cap = worklist_cap;
+    p.dump = dump; p.dump_pitch = dump_pitch;
     const size_t smem = 1024 + (size_t)ST * STAGE_BYTES + 32 * sizeof(uint64_t);
-    static bool attr_set = false;      // once per process; keeps the call legal inside stream capture
-    if (!attr_set) {
-        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_tc_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    const int which = dump ? 1 : 0;
+    if (dev < 64 && !g_attr_set[dev][which]) {      // once per device; keeps the call legal inside stream capture
+        if (dump) LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_tc_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_tc_assign<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_attr_set[dev][which] = true;
     }
     const int n_rt = (int)((M + BM - 1) / BM);
     const int grid = n_rt < sm_count() ? n_rt : sm_count();
-    k_tc_assign<<<grid, TC_THREADS, smem, st>>>(mx1, mx2, mc1, mc2, p);
+    if (dump) k_tc_assign<true><<<grid, TC_THREADS, smem, st>>>(mx1, mx2, mc1, mc2, p);
+    else k_tc_assign<false><<<grid, TC_THREADS, smem, st>>>(mx1, mx2, mc1, mc2, p);
     return check_launch("k_tc_assign");
+}
+}  // namespace leida
+
+extern "C" int leida_kmeans_tc_assign(const void* X1, const void* X2, const double* xnorm, int64_t M, int N, const void* C1,
+                                      const void* C2, int64_t c_rows, const int32_t* plan, const int32_t* tile_first,
+                                      const int32_t* tile_count, const int32_t* prun, int32_t* labels_new,
+                                      int32_t* worklist, int64_t worklist_cap, double tau, leida_stream_t stream) {
+    return launch_tc_assign(X1, X2, xnorm, M, N, C1, C2, c_rows, plan, tile_first, tile_count, prun, labels_new, worklist,
+                            worklist_cap, tau, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int leida_kmeans_tc_scores(const void* X1, const void* X2, const double* xnorm, int64_t M, int N, const void* C1,
+                                      const void* C2, int64_t c_rows, const int32_t* plan, const int32_t* tile_first,
+                                      const int32_t* tile_count, const int32_t* prun, int32_t* labels_new,
+                                      int32_t* worklist, int64_t worklist_cap, float* scores, int64_t score_pitch,
+                                      leida_stream_t stream) {
+    LEIDA_REQUIRE(scores && score_pitch >= c_rows, "scores (M, score_pitch >= c_rows)");
+    return launch_tc_assign(X1, X2, xnorm, M, N, C1, C2, c_rows, plan, tile_first, tile_count, prun, labels_new, worklist,
+                            worklist_cap, 0.0, scores, score_pitch, (cudaStream_t)stream);
 }
 
 extern "C" int leida_kmeans_tc_apply(const float* X, int64_t M, int N, int64_t x_pitch, int unit_rows, int n_runs_bound,

@@ -21,7 +21,7 @@ lib = ctypes.CDLL(LIB_PATH)
 LEIDA_KM_FRAC_BITS = 40
 STATE_WORDS = 16
 ST_CHANGED, ST_DIST_HI, ST_DIST_LO, ST_RECHECKED, ST_ACTIVE, ST_PASSES, ST_EMPTY, ST_K = range(8)
-ST_RECHECK_TOTAL, ST_CHANGED_TOTAL = 8, 9
+ST_RECHECK_TOTAL, ST_CHANGED_TOTAL, ST_TAU_WATCH = 8, 9, 10
 KM_MAX_K = 64
 
 _P = c_void_p
@@ -48,7 +48,9 @@ SIGNATURES = {
     "leida_kmeans_tc_pitch": (c_int64, [c_int]),
     "leida_kmeans_tc_split_rows": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P]),
     "leida_kmeans_tc_plan": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
-    "leida_kmeans_tc_assign": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "leida_kmeans_tc_assign": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, c_double, _P]),
+    "leida_kmeans_tc_tau": (c_double, [c_int]),
+    "leida_kmeans_tc_scores": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P]),
     "leida_kmeans_tc_apply": (c_int, [_P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_update": (c_int, [c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_update_peers": (c_int, [c_int, _P, _P, c_int, c_int64, _P, c_int, c_int64, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),

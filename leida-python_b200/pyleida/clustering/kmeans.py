@@ -54,15 +54,36 @@ class KMeansEngine:
             packed = torch.empty((src.shape[0], xp), dtype=torch.float32, device=src.device)
             nv.call("leida_kmeans_pack_rows", nv.ptr(src), src.shape[0], N, src.shape[1], nv.ptr(packed), xp, nv.stream())
             X = packed
-        self.X, self.N, self.XP = X, N, xp
+        self.N, self.XP = N, xp
         self.M = int(X.shape[0])
         self.comm = comm if comm is not None else Comm()
         self.row_lo = int(row_lo)
         self.m_global = int(m_global) if m_global is not None else self.M
+        # Range of the fixed-point centroid sums (int64, 2^40 per unit): exact while |x| <= 1 and a cluster holds fewer
+        # than 2^22 rows.  LEiDA eigenvectors are unit vectors; any other data is brought into range by ONE global
+        # power-of-two factor (exact in float32; cosine assignment and distortion do not depend on it, and the
+        # centroids are scaled back exactly where they leave the engine).  Elements below 2^-40 of the largest
+        # magnitude do not contribute to the sums.
+        if self.m_global >= (1 << 22):
+            raise ValueError("KMeansEngine supports fewer than 2^22 rows in total (int64 fixed-point centroid sums)")
+        amax = 0.0
+        if self.M > 0:
+            mn, mx = X.aminmax()                          # no (M, pitch) temporary
+            amax = max(-float(mn), float(mx))
+        if self.comm.world > 1:
+            t = torch.tensor([amax], dtype=torch.float64, device=X.device if self.comm.backend == "nccl" else "cpu")
+            amax = float(self.comm.all_reduce_max_(t).item())
+        if not np.isfinite(amax):
+            raise ValueError("rows must be finite")
+        self.scale = 1.0
+        if amax > 1.0 or 0.0 < amax < 2.0 ** -8:
+            self.scale = float(2.0 ** np.ceil(np.log2(amax)))
+            X = X * (1.0 / self.scale)
+        self.X = X
         self.xnorm = torch.empty(max(self.M, 1), dtype=torch.float64, device=X.device)
         nv.call("leida_kmeans_row_norms", nv.ptr(X), self.M, N, xp, nv.ptr(self.xnorm), nv.stream())
-        # |x| <= 1 everywhere (LEiDA eigenvectors are unit vectors) lets leida_kmeans_tc_apply quantise on the FMA pipe
-        self.unit_rows = bool(self.M > 0 and float(X.abs().max()) <= 1.0)
+        # |x| <= 1 everywhere lets leida_kmeans_tc_apply quantise on the FMA pipe
+        self.unit_rows = self.M > 0
 
     # ------------------------------------------------------------------------------------------
     def _tc_operands(self):
@@ -136,9 +157,11 @@ class KMeansEngine:
         acc = red_local[:n_acc].view(CR, AP)
         state = red_local[n_acc:].view(R, nv.STATE_WORDS)
         labels = torch.empty((R, self.M), dtype=torch.int32, device=dev)
-        cap = int(min(max(R * self.M // 8, 1 << 16), 1 << 24))    # (run,row) pairs queued for the fp64 re-check per pass
+        # (run,row) pairs queued for the fp64 re-check per pass: 32-byte entries; a pass needs a fraction of a percent of
+        # R*M, and a full queue only costs time (the re-check then scans for the unlisted marks)
+        cap = int(min(max(R * self.M // 64, 1 << 16), 1 << 23))
         cap = int(os.environ.get("LEIDA_KMEANS_WORKLIST_CAP", cap))   # tests shrink it to exercise the overflow path
-        worklist = torch.empty(2 * cap + 8, dtype=torch.int32, device=dev)
+        worklist = torch.empty(8 * cap + 8, dtype=torch.int32, device=dev)
         worklist[:8].zero_()
         n_active = torch.zeros(8, dtype=torch.int32, device=dev)
         mailbox = torch.zeros(4, dtype=torch.int32, pin_memory=True)   # written by the last CTA of leida_kmeans_update
@@ -179,6 +202,8 @@ class KMeansEngine:
             profile.setdefault(name, []).append((e0, e1))
 
         tc = assign == "tc"
+        # trust threshold of the tensor-core argmax: the library's measured bound, optionally scaled (experiments only)
+        tau = float(nv.lib.leida_kmeans_tc_tau(self.N)) * float(os.environ.get("LEIDA_TC_TAU_SCALE", "1"))
         if tc:
             x1, x2, npk = self._tc_operands()
             # packed columns: every run owns a slot of read_width(K) <= 2K columns; tiles hold one slot width each,
@@ -218,7 +243,7 @@ class KMeansEngine:
                     f = fast[("assign", stq)] = nv.prepared(
                         "leida_kmeans_tc_assign", nv.ptr(x1), nv.ptr(x2), nv.ptr(self.xnorm), self.M, self.N, nv.ptr(c1), nv.ptr(c2),
                         c_rows, nv.ptr(plan), nv.ptr(tile_first), nv.ptr(tile_count), nv.ptr(prun), nv.ptr(labels_new),
-                        nv.ptr(worklist), cap, stq)
+                        nv.ptr(worklist), cap, tau, stq)
                 f()
                 return
             for (a, b, kmax) in groups:
@@ -349,6 +374,14 @@ class KMeansEngine:
         inv[np.asarray(order)] = np.arange(R)
         out = BatchResult(self, inv, ks, crow0, cent, labels, inertia, st_host[:, nv.ST_PASSES].copy(), empty, counts,
                           launches, passes)
+        # largest tensor-core margin (fraction of the trust threshold) at which the fp64 re-check overruled the tensor-core
+        # argmax: the error bound is sound while this stays well below 1 (see kmeans_tc.cu: default_tau)
+        out.tau = tau
+        out.tau_watch = float(st_host[:, nv.ST_TAU_WATCH].astype(np.int32).view(np.float32).max()) if tc else 0.0
+        if out.tau_watch > 0.5:
+            warnings.warn(f"tensor-core trust threshold is thin: an argmax with margin {out.tau_watch:.2f} x threshold was "
+                          "overruled in fp64; results are still exact for every re-checked pair, but rerun with "
+                          "LEIDA_TC_TAU_SCALE=2 (or LEIDA_KMEANS_ASSIGN=simt) and report this data set")
         out.rechecked_total = int(st_host[:, nv.ST_RECHECK_TOTAL].sum())
         out.changed_total = int(st_host[:, nv.ST_CHANGED_TOTAL].sum())
         out.assign = assign
@@ -390,7 +423,8 @@ class BatchResult:
 
     def centers_device(self, i):
         j = self._inv[i]
-        return self._cent[int(self._crow0[j]):int(self._crow0[j] + self._ks[j]), :self.engine.N]
+        c = self._cent[int(self._crow0[j]):int(self._crow0[j] + self._ks[j]), :self.engine.N]
+        return c if self.engine.scale == 1.0 else c * self.engine.scale
 
     def labels_device(self, i):
         return self._labels[int(self._inv[i])]
@@ -401,7 +435,7 @@ class BatchResult:
         a, b = int(self._crow0[j]), int(self._crow0[j] + self._ks[j])
         sums = self._acc[a:b, :self.engine.N].cpu().numpy().astype(np.float64) * 2.0 ** -nv.LEIDA_KM_FRAC_BITS
         with np.errstate(divide="ignore", invalid="ignore"):
-            return sums / self._counts[a:b].astype(np.float64)[:, None]
+            return sums / self._counts[a:b].astype(np.float64)[:, None] * self.engine.scale
 
 
 def _remap_permutation(counts):
@@ -492,7 +526,16 @@ class KMeansLeida:
             raise NotImplementedError("only metric='cosine' runs on the GPU path")
         eng = engine if engine is not None else KMeansEngine(y)
         M = eng.m_global
-        inits = list(init_indices) if init_indices is not None else _draw_inits(M, self._k_, self._n_init_, random_state)
+        if init_indices is not None:
+            inits = list(init_indices)
+        elif eng.comm.world > 1:                       # one draw for the whole job (rank 0's RNG), see sweep_runs
+            flat = np.zeros(self._n_init_ * self._k_, dtype=np.int64)
+            if eng.comm.rank == 0:
+                flat[:] = np.concatenate(_draw_inits(M, self._k_, self._n_init_, random_state))
+            flat = eng.comm.bcast0_int64(flat)
+            inits = [flat[r * self._k_:(r + 1) * self._k_].copy() for r in range(self._n_init_)]
+        else:
+            inits = _draw_inits(M, self._k_, self._n_init_, random_state)
         if len(inits) != self._n_init_:
             raise ValueError("init_indices must hold n_init index arrays")
         first = _dedupe(inits)
@@ -553,18 +596,39 @@ def score_sample(M, drawn=None):
     return drawn if drawn is not None else np.random.choice(np.arange(M), size=30_000, replace=False)
 
 
-def sweep_runs(M, K_min, K_max, n_init, random_state=None, init_indices=None):
+def sweep_runs(M, K_min, K_max, n_init, random_state=None, init_indices=None, comm=None):
     """The (K, initial rows) runs of a K sweep in the reference's draw order (clustering/_clustering.py:
     318-329), identical restarts removed.  Returns (runs, plan): plan[k][r] = index into runs of
-    restart r of K=k."""
+    restart r of K=k.  With several ranks the draws are made on rank 0 only and broadcast: every process has
+    its own numpy global RNG, and ranks that seeded different initial rows would reduce unrelated centroids."""
     sweep_runs.last_sample = None
-    if M > 30_000 and init_indices is None:
-        # :318-320 -- the reference draws its score sub-sample here; repeating the draw keeps the
-        # global RNG stream (and therefore every later initial centroid) aligned with it.
-        sweep_runs.last_sample = np.random.choice(np.arange(M), size=30_000, replace=False)
+    multi = comm is not None and comm.world > 1
+    drawn = None
+    if init_indices is None and (not multi or comm.rank == 0):
+        drawn = {}
+        if M > 30_000:
+            # :318-320 -- the reference draws its score sub-sample here; repeating the draw keeps the
+            # global RNG stream (and therefore every later initial centroid) aligned with it.
+            sweep_runs.last_sample = np.random.choice(np.arange(M), size=30_000, replace=False)
+        for k in range(K_min, K_max + 1):
+            drawn[k] = _draw_inits(M, k, n_init, random_state)
+    if init_indices is None and multi:
+        ks = list(range(K_min, K_max + 1))
+        n_sample = 30_000 if M > 30_000 else 0
+        flat = np.zeros(n_sample + n_init * sum(ks), dtype=np.int64)
+        if comm.rank == 0:
+            parts = [sweep_runs.last_sample] if n_sample else []
+            parts += [np.asarray(idx, dtype=np.int64) for k in ks for idx in drawn[k]]
+            flat[:] = np.concatenate(parts)
+        flat = comm.bcast0_int64(flat)
+        sweep_runs.last_sample = flat[:n_sample].copy() if n_sample else None
+        drawn, o = {}, n_sample
+        for k in ks:
+            drawn[k] = [flat[o + r * k: o + (r + 1) * k].copy() for r in range(n_init)]
+            o += n_init * k
     runs, plan = [], {}
     for k in range(K_min, K_max + 1):                                          # :326
-        inits = list(init_indices[k]) if init_indices is not None else _draw_inits(M, k, n_init, random_state)
+        inits = list(init_indices[k]) if init_indices is not None else drawn[k]
         if len(inits) != n_init:
             raise ValueError(f"init_indices[{k}] must hold n_init index arrays")
         first = _dedupe(inits)
@@ -609,6 +673,8 @@ def select_models(engine, res, plan, n_init, to_host=True, stacked=False):
     nv.call("leida_remap_labels_batch_i32", nv.ptr(res._labels), M, n_out, nv.ptr(d_rows), nv.ptr(d_luts), kmax,
             nv.ptr(labels_all), nv.stream())
     centers_all = res._cent[d_crow][:, :engine.N]                   # (sum K, N) in the relabelled order
+    if engine.scale != 1.0:
+        centers_all = centers_all * engine.scale
     models, off = {}, 0
     for c, (k, r, best_init, inertias, lut, order) in enumerate(picks):
         km = KMeansLeida(k=k, n_init=n_init, n_iter=1_000)
@@ -636,7 +702,7 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
     if engine is None:
         X = np.array(eigens_dataset.iloc[:, 2:], dtype=np.float32)            # :316
         engine = KMeansEngine(X)
-    runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices)
+    runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices, comm=engine.comm)
     res = engine.run(runs, n_iter=1_000, centroid_update=centroid_update)
     by_k = select_models(engine, res, plan, n_init)
     ks = list(range(K_min, K_max + 1))

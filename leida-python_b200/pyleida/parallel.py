@@ -42,6 +42,30 @@ class Comm:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
 
+    @property
+    def backend(self):
+        return self._dist.get_backend(self.group) if self.world > 1 else "none"
+
+    def _device(self):
+        import torch
+        return torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
+
+    def all_reduce_max_(self, t):
+        if self.world > 1:
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def bcast0_int64(self, arr):
+        """numpy int64 array of rank 0 on every rank (the other ranks pass an array of the same shape)."""
+        import torch
+        if self.world == 1:
+            return arr
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self._device())
+        if self.rank != 0:
+            t.zero_()
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
     def all_gather_int(self, value):
         """Gather one python int from every rank -> list."""
         import torch

@@ -36,16 +36,29 @@ def run_device(blocks, n_rois, seg_off, seg_rows, K_min=2, K_max=20, n_init=15, 
     M = int(sum(rows))
     x32 = torch.empty((M, xp), dtype=torch.float32, device=dev)
     lei64 = torch.empty((M, N), dtype=torch.float64, device=dev) if keep_f64 else None
-    r0 = 0
-    for b, nr in zip(blocks, rows):                                        # stage 1+2 (_leida.py:287-289)
-        leading_eigenvectors(b, want_f64=keep_f64, out_f64=None if lei64 is None else lei64[r0:r0 + nr],
-                             out_f32=x32[r0:r0 + nr])
-        r0 += nr
+    def timed(name, fn):
+        """bench.py's live per-kernel timing (same convention as KMeansEngine.run)"""
+        if profile is None or not (profile.get("*") or name in profile):
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        profile.setdefault(name, []).append((e0, e1))
+        return out
+
+    def stage12():
+        r0 = 0
+        for b, nr in zip(blocks, rows):                                    # stage 1+2 (_leida.py:287-289)
+            leading_eigenvectors(b, want_f64=keep_f64, out_f64=None if lei64 is None else lei64[r0:r0 + nr],
+                                 out_f32=x32[r0:r0 + nr])
+            r0 += nr
+    timed("stage12", stage12)
     if f64_sink is not None and lei64 is not None:
         f64_sink(lei64)
     off = row_offsets(comm.all_gather_int(M))
     engine = KMeansEngine(x32, n_features=N, comm=comm, row_lo=int(off[comm.rank]), m_global=int(off[-1]))
-    runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices)
+    runs, plan = sweep_runs(engine.m_global, K_min, K_max, n_init, random_state, init_indices, comm=comm)
     batch = engine.run(runs, n_iter=1_000, centroid_update=centroid_update, profile=profile)   # stage 3 (:314-321)
     models, labels = select_models(engine, batch, plan, n_init, to_host=False, stacked=True)   # labels: (n_cols, M) int32
     ks = list(range(K_min, K_max + 1))
@@ -56,8 +69,9 @@ def run_device(blocks, n_rois, seg_off, seg_rows, K_min=2, K_max=20, n_init=15, 
     runs_t = torch.empty((len(ks), G, kmax), dtype=torch.int32, device=dev)
     trans = torch.empty((len(ks), G, kmax, kmax), dtype=torch.int32, device=dev)
     d_k = torch.from_numpy(col_k).to(dev)
-    nv.call("leida_dynamics_counts_i32", nv.ptr(labels), M, len(ks), nv.ptr(d_k), nv.ptr(seg_off), nv.ptr(seg_rows), G,
-            kmax, nv.ptr(occ), nv.ptr(runs_t), nv.ptr(trans), nv.stream())   # stage 4 (:326-331)
+    timed("metrics", lambda: nv.call(
+        "leida_dynamics_counts_i32", nv.ptr(labels), M, len(ks), nv.ptr(d_k), nv.ptr(seg_off), nv.ptr(seg_rows), G,
+        kmax, nv.ptr(occ), nv.ptr(runs_t), nv.ptr(trans), nv.stream()))   # stage 4 (:326-331)
     out = DeviceResult()
     out.lei64, out.x32, out.engine, out.batch, out.models = lei64, x32, engine, batch, models
     out.labels, out.col_k, out.occ, out.runs, out.trans = labels, col_k, occ, runs_t, trans

@@ -1,0 +1,185 @@
+"""GPU parity tests at the sizes the benchmark runs at (BASELINE configs 2 and 3), through the C-ABI:
+  * full Lloyd runs to convergence on M = 119 800 x 116 rows against the CPU oracle (labels, pass counts, inertia);
+  * every pass's labels on M ~ 200 000 x 400 rows against an independent fp64 brute-force Lloyd (this is what validates
+    the tensor-core trust threshold at N = 400);
+  * the measured error of the tensor-core score against fp64, which the threshold is derived from;
+  * compute_dynamics_metrics called directly on a predictions DataFrame against the golden tables;
+  * unnormalised rows (the engine's power-of-two range scaling).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pyleida
+    return pyleida
+
+
+@pytest.fixture(scope="module")
+def O():
+    import leida_oracle
+    return leida_oracle
+
+
+def _rows(n_subjects, n_rois, kind):
+    """fp32 eigenvector rows of a synthetic data set, made by the CUDA stage 1+2 (device tensor, host copy)."""
+    import torch
+    from pyleida import synthetic
+    from pyleida.signal_tools.phase import leading_eigenvectors
+    ts, _ = synthetic.make_shard(n_subjects, n_rois, 1200, 0, n_subjects, kind)
+    x = torch.from_numpy(np.stack(list(ts.values()))).cuda()
+    _, xf = leading_eigenvectors(x, want_f64=False)
+    return xf, xf[:, :n_rois].cpu().numpy()
+
+
+def _same_partition_fraction(got, ref, k):
+    """Fraction of rows on which `got` (any cluster numbering) induces the partition `ref`: clusters are matched through
+    the first row of each `got` cluster."""
+    u, first = np.unique(got, return_index=True)
+    lut = np.full(k, -1, dtype=np.int64)
+    lut[u] = ref[first]
+    return float((lut[got] == ref).mean())
+
+
+@pytest.mark.parametrize("kind,ks,n_iter", [("states", (5, 12, 20), 1000), ("iid", (4, 11), 30)])
+def test_config2_size_full_lloyd_vs_oracle(P, O, kind, ks, n_iter):
+    """M = 119 800 x 116 (the config-2 data set): whole Lloyd runs against oracle.KMeansLeida on the SAME fp32 rows and
+    the same initial rows.  centroid_update='reference' (numpy's sequential float32 member sums, bit for bit): identical
+    labels, identical iteration counts, inertia to 1e-6.  centroid_update='exact' (the production mode: exactly rounded
+    means, shard-count invariant) differs from the reference only through the rounding noise of the reference's own
+    float32 sums (~1e-6 relative on a centroid at this size), which can move rows that sit on a cluster boundary to
+    within that noise: at least 99.9 % of the rows end in the same cluster.  iid rows (the worst case for margins
+    and iteration counts) are capped at 30 iterations on both sides."""
+    from pyleida.clustering.kmeans import KMeansEngine
+    xf, X = _rows(100, 116, kind)
+    eng = KMeansEngine(xf, n_features=116)
+    rng = np.random.default_rng(5)
+    inits = [rng.choice(X.shape[0], size=k, replace=False).astype(np.int64) for k in ks]
+    runs = [(k, idx) for k, idx in zip(ks, inits)]
+    strict = eng.run(runs, n_iter=n_iter, centroid_update="reference")
+    exact = eng.run(runs, n_iter=n_iter)
+    assert strict.tau_watch <= 0.5 and exact.tau_watch <= 0.5
+    for i, (k, idx) in enumerate(runs):
+        ref = O.KMeansLeida(k=k, n_init=1, n_iter=n_iter).fit(X, init_indices=[idx])
+        got = strict.labels_device(i).cpu().numpy()
+        assert _same_partition_fraction(got, ref.labels_, k) == 1.0, (kind, k)
+        assert strict.passes(i) == ref.n_iter_runs_[0] + 1, (kind, k)         # + the initial assignment pass
+        assert strict.inertia(i) == pytest.approx(float(ref.inertia_), rel=1e-6)
+        frac = _same_partition_fraction(exact.labels_device(i).cpu().numpy(), ref.labels_, k)
+        assert frac >= 0.999, (kind, k, frac)
+        assert exact.inertia(i) == pytest.approx(float(ref.inertia_), rel=1e-4)
+
+
+def _lloyd_fp64(X32, init_rows, n_passes):
+    """Independent brute-force Lloyd in torch fp64 (clustering/_clustering.py:105-133): labels after the initial
+    assignment and after each of n_passes iterations."""
+    import torch
+    X = X32.double()
+    xn = X.norm(dim=1)
+    C = X32[init_rows].clone()                                             # fp32 centroids (:105-108)
+    out = []
+    for it in range(n_passes + 1):
+        Cd = C.double()
+        d = 1.0 - (X @ Cd.T) / (xn[:, None] * Cd.norm(dim=1)[None, :])
+        lab = d.argmin(dim=1)
+        out.append(lab)
+        K = C.shape[0]
+        sums = torch.zeros((K, X.shape[1]), dtype=torch.float64, device=X.device).index_add_(0, lab, X)
+        cnt = torch.bincount(lab, minlength=K).double()
+        C = (sums / cnt[:, None]).float()                                  # member means rounded to fp32 (:120-125)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["states", "iid"])
+def test_config3_shape_every_pass_vs_fp64_bruteforce(P, kind):
+    """M = 203 660 x 400 (config-3 row width), K in {7, 20}: the labels after EVERY one of the first 10 Lloyd passes
+    equal an independent fp64 brute force -- the tensor-core path (trust threshold + fp64 re-check of the candidate
+    clusters) is the fp64 argmin, pass by pass, at N = 400."""
+    import torch
+    from pyleida.clustering.kmeans import KMeansEngine
+    xf, _ = _rows(170, 400, kind)
+    eng = KMeansEngine(xf, n_features=400)
+    rng = np.random.default_rng(11)
+    runs = [(k, rng.choice(eng.M, size=k, replace=False).astype(np.int64)) for k in (7, 20)]
+    X32 = xf[:, :400].contiguous()
+    want = [_lloyd_fp64(X32, torch.from_numpy(idx).cuda(), 10) for _, idx in runs]
+    for p in range(0, 11):
+        res = eng.run(runs, n_iter=p)
+        assert res.tau_watch <= 0.5
+        for i in range(len(runs)):
+            got = res.labels_device(i).long()
+            bad = int((got != want[i][p]).sum())
+            assert bad == 0, (kind, runs[i][0], p, bad)
+
+
+def test_tc_score_error_within_bound(P):
+    """The trust threshold must cover the measured tensor-core score error with the stated safety factor: observed
+    max |S_tc - S_fp64| / |x| over ~5e7 scores per case, times 2 (two scores are compared) times 2 (safety) <= tau."""
+    import importlib.util
+    import torch
+    from pyleida import _native as nv, synthetic
+    from pyleida.clustering.kmeans import KMeansEngine, sweep_runs
+    from pyleida.signal_tools.phase import leading_eigenvectors
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("tc_score_error", os.path.join(root, "tools", "tc_score_error.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    for N, kind in ((116, "iid"), (400, "states"), (1000, "iid")):
+        S = 12
+        ts, _ = synthetic.make_shard(S, N, 1200, 0, S, kind)
+        x = torch.from_numpy(np.stack(list(ts.values()))).cuda()
+        _, xf = leading_eigenvectors(x, want_f64=False)
+        eng = KMeansEngine(xf, n_features=N)
+        inits = synthetic.init_indices(eng.M, 2, 20, 15, seed=0)
+        runs, _ = sweep_runs(eng.M, 2, 20, 15, None, inits)
+        res = eng.run(runs, n_iter=2)
+        worst, rms, q, pairs = tool.score_errors(eng, res._cent, res._ks.astype(np.int64), res._crow0.astype(np.int64))
+        tau = float(nv.lib.leida_kmeans_tc_tau(N))
+        assert 4.0 * worst <= tau, (N, kind, worst, tau)
+
+
+def test_compute_dynamics_metrics_direct_golden(P):
+    """compute_dynamics_metrics(predictions DataFrame) (dynamics_metrics/_dynamics_metrics.py:11-105) called directly,
+    against the tables the unmodified reference produced for the same labels (tests/golden/pipeline_case.npz)."""
+    import pandas as pd
+    g = np.load(os.path.join(GOLD, "pipeline_case.npz"), allow_pickle=True)
+    ks = [int(k) for k in g["perf_k"]]
+    df = pd.DataFrame({"subject_id": g["subject_id"], "condition": g["condition"]})
+    for k in ks:
+        df[f"k_{k}"] = g[f"labels_k{k}"]
+    out = P.dynamics_metrics.compute_dynamics_metrics(df, TR=0.72)
+    assert set(out.keys()) == {"dwell_times", "occupancies", "transitions"}
+    for k in ks:
+        for name in ("occupancies", "dwell_times", "transitions"):
+            tab = out[name][f"k_{k}"]
+            assert np.array_equal(tab.iloc[:, 2:].values, g[f"{name}_k{k}"]), (k, name)
+            assert list(tab.columns[2:]) == list(g[f"{name}_k{k}_cols"])
+            assert list(tab.subject_id) == list(g[f"{name}_k{k}_subject"])
+            assert list(tab.condition) == list(g[f"{name}_k{k}_condition"])
+    # the reference renames the first two columns in place when they are not called subject_id / condition (:58-61)
+    df2 = df.rename(columns={"subject_id": "id", "condition": "group"})
+    out2 = P.dynamics_metrics.compute_dynamics_metrics(df2)
+    assert list(df2.columns[:2]) == ["subject_id", "condition"]
+    assert np.array_equal(out2["occupancies"][f"k_{ks[0]}"].iloc[:, 2:].values, g[f"occupancies_k{ks[0]}"])
+
+
+def test_unnormalised_rows_are_scaled_into_range(P, O):
+    """Rows far outside [-1, 1] (the advisor's 'amplitude 1e4' case) and tiny rows: the engine applies one power-of-two
+    factor, so labels equal the oracle's and the centroids come back in the caller's units."""
+    rng = np.random.default_rng(21)
+    base = rng.standard_normal((6000, 24)).astype(np.float32)
+    for amp in (1.0e4, 3.0e-7):
+        X = (base * np.float32(amp)).astype(np.float32)
+        idx = [rng.choice(X.shape[0], size=5, replace=False)]
+        km = P.clustering.KMeansLeida(k=5, n_init=1).fit(X, init_indices=idx)
+        ref = O.KMeansLeida(k=5, n_init=1).fit(X, init_indices=idx)
+        assert np.array_equal(km.labels_, ref.labels_), amp
+        assert np.allclose(km.cluster_centers_, ref.cluster_centers_, rtol=2e-6, atol=0), amp
+        assert km.inertia_ == pytest.approx(float(ref.inertia_), rel=1e-6)

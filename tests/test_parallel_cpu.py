@@ -21,6 +21,18 @@ def _load_parallel():
     return mod
 
 
+def _load_kmeans_host():
+    """sweep_runs / _draw_inits / _dedupe of clustering/kmeans.py without importing the CUDA-backed package: the
+    functions are pure numpy, so their source is executed in a scratch namespace."""
+    import ast
+    src = open(os.path.join(ROOT, "leida-python_b200", "pyleida", "clustering", "kmeans.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("sweep_runs", "_draw_inits", "_dedupe")]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "kmeans_host", "exec"), ns)
+    return ns
+
+
 def test_shard_bounds_cover_everything():
     P = _load_parallel()
     for n in (0, 1, 7, 100, 1001):
@@ -55,6 +67,24 @@ def _worker(rank, world, port, q):
         part = torch.from_numpy(q40[lo:hi].sum(0))
         comm.all_reduce_sum_(part)
         assert np.array_equal(part.numpy(), q40.sum(0))
+        # rank 0's values reach every rank; max-reduce
+        mine = np.arange(7, dtype=np.int64) * (rank + 1) + 100 * rank
+        assert np.array_equal(comm.bcast0_int64(mine), np.arange(7, dtype=np.int64))
+        assert float(comm.all_reduce_max_(torch.tensor([float(rank)], dtype=torch.float64)).item()) == world - 1
+        assert comm.backend == "gloo"
+        # k-means initial rows with random_state=None: every process has its own numpy global RNG, so the draws are
+        # made on rank 0 and broadcast (ranks that seed different rows reduce unrelated centroids)
+        K = _load_kmeans_host()
+        np.random.seed(1234 + rank)                      # deliberately different streams
+        runs, plan = K["sweep_runs"](40_000, 2, 5, 3, None, None, comm=comm)
+        flat = np.concatenate([np.asarray(r[1], dtype=np.int64) for r in runs])
+        ref = torch.from_numpy(flat.copy())
+        dist.broadcast(ref, src=0)
+        assert np.array_equal(flat, ref.numpy()), "ranks drew different initial rows"
+        smp = torch.from_numpy(np.asarray(K["sweep_runs"].last_sample, dtype=np.int64).copy())
+        ref = smp.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(smp, ref) and smp.numel() == 30_000
         comm.barrier()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover

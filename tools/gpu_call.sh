@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 GPU session script (run under gpurun from the repo root).  Usage: tools/gpu_call.sh <tag> <stage...>
+set -u
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+for stage in "$@"; do
+  case $stage in
+    tests)     timeout 900 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests rc=$?" ;;
+    newtests)  timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -q > $OUT/newtests.log 2>&1; echo "newtests rc=$?" ;;
+    scoreerr)  timeout 600 python tools/tc_score_error.py > $OUT/tc_score_error.txt 2> $OUT/tc_score_error.err; echo "scoreerr rc=$?" ;;
+    bench)     timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" ;;
+    bench_tau) for s in 0.5 0.25 0.125; do LEIDA_TC_TAU_SCALE=$s timeout 600 python bench.py --steps 2 --warmup 2 --no-cpu --no-secondary > $OUT/bench_tau$s.json 2> $OUT/bench_tau$s.err; echo "bench_tau$s rc=$?"; done ;;
+    bench2)    timeout 600 python bench.py --config config2 --steps 5 --warmup 3 --no-cpu > $OUT/bench_config2.json 2> $OUT/bench_config2.err; echo "bench2 rc=$?" ;;
+    ref)       timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?" ;;
+    ncu_list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-secondary > $OUT/ncu_list.log 2>&1; echo "ncu_list rc=$?" ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+tail -n 5 $OUT/*.log 2>/dev/null | cut -c1-300
