@@ -240,17 +240,29 @@ int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32_t* run_cro
                         float* cent, double* cnorm, int64_t* state, int n_iter,
                         int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
                         int32_t* mailbox, leida_stream_t stream);
-/* Same, with the all-reduce fused in (several GPUs of one node): peer_bufs is a DEVICE array of n_peers
- * pointers, one per rank (this rank included), each to that rank's exchange buffer -- its acc words
- * followed, from word state_offset_words, by its state words -- mapped into this process (CUDA IPC /
- * symmetric memory).  The kernel reads the buffers in place over NVLink and sums them (int64: exact, order
- * free), and only for the runs that are still active.  The caller orders the ranks: every rank's buffer is
- * complete before any rank's call starts, and is not rewritten before every rank's call has finished. */
+/* Same, with the all-reduce fused in (several GPUs of one node, SURVEY 8e): peer_bufs is a DEVICE array of n_peers
+ * pointers, one per rank (this rank included), each to that rank's exchange buffer -- its acc words followed, from
+ * word state_offset_words, by its state words -- mapped into this process (symmetric memory).  The kernel sums the
+ * ranks' words itself (int64: exact, order free), only for the runs that are still active: with multicast_buf != NULL
+ * (the NVSwitch multicast mapping of the same buffers) by one multimem.ld_reduce.add.u64 per word -- the switch adds --
+ * else by one load per rank over NVLink.  flags/seq != NULL: the kernel waits until flags[r] >= *seq + 1 for every rank
+ * r (written by the ranks' leida_kmeans_exchange_publish of this pass) and increments *seq when done; NULL: the caller
+ * has ordered the ranks (every buffer complete before any rank's call starts). */
 int leida_kmeans_update_peers(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
-                              const int64_t* const* peer_bufs, int n_peers, int64_t state_offset_words,
+                              const int64_t* const* peer_bufs, int n_peers, const int64_t* multicast_buf,
+                              int64_t state_offset_words, const uint64_t* flags, const uint64_t* seq,
                               float* cent, double* cnorm, int64_t* state, int n_iter,
                               int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
                               int32_t* mailbox, leida_stream_t stream);
+/* Publish this rank's words of one pass: copies the acc rows of the still-active runs and all state words from
+ * local_words (acc words, then from n_acc_words the state words) to exchange_half (one half of this rank's symmetric
+ * buffer, same layout), then writes ++*seq into slot my_rank of every rank's flag array (peer_flags: DEVICE array of
+ * n_peers pointers) with release semantics at system scope.  Halves alternate pass by pass; seq (device uint64) and
+ * counter (device int32, zero) persist across passes. */
+int leida_kmeans_exchange_publish(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int64_t x_pitch,
+                                  const int64_t* local_words, int64_t n_acc_words, int64_t* exchange_half,
+                                  uint64_t* const* peer_flags, int n_peers, int my_rank, uint64_t* seq,
+                                  int32_t* counter, leida_stream_t stream);
 /* n_active_out: device int32[8], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
  * [2] = runs still active after this call, [3] = calls completed, [4] = first all-stopped call).  mailbox (may be NULL): HOST-visible (pinned, mapped),
  * 8-byte aligned; the last CTA publishes ONE 64-bit word there -- bits 0-15 runs still active, bits 16-39 number

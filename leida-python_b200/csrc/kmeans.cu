@@ -438,23 +438,118 @@ __global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
 }
 
 // Control + centroid update, one CTA per run.
-// Where k_update reads the job-wide sums from: one buffer (single GPU, or after an NCCL all-reduce), or the
-// exchange buffers of all ranks, read in place over NVLink and summed here (int64: exact, any order) -- the
-// all-reduce fused into its consumer, and only for the runs that are still active.
+// Where k_update reads the job-wide sums from:
+//   * one buffer (single GPU, or after an NCCL all-reduce);
+//   * the exchange buffers of all ranks in symmetric memory, summed here (int64: exact, any order) -- the all-reduce
+//     fused into its consumer, and only for the runs that are still active: either ONE multimem.ld_reduce per word
+//     through the NVSwitch multicast mapping (the switch adds the ranks' words), or one load per rank over NVLink.
+// With an exchange the kernel first waits until every rank has published this pass (flags written by
+// k_exchange_publish on the peers, see there).
 struct ReducedSource {
     const long long* acc;             // n_peers == 0
     const long long* state;
     const long long* const* peers;    // n_peers > 0: device array of every rank's buffer (acc words, then state words)
     int n_peers;
     long long state_off;
+    const long long* mc;              // multicast address of the same buffer (multimem.ld_reduce), or null
+    const unsigned long long* flags;  // this rank's flag words, one per rank, or null (the caller ordered the ranks)
+    const unsigned long long* seq;    // device counter: passes consumed so far; this pass waits for flags >= *seq + 1
     __device__ __forceinline__ long long sum(long long word) const {
+        if (mc) {
+            unsigned long long v;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(mc + word) : "memory");
+            return (long long)v;
+        }
         long long v = 0;
         for (int p = 0; p < n_peers; ++p) v += *reinterpret_cast<const volatile long long*>(peers[p] + word);
         return v;
     }
     __device__ __forceinline__ long long acc_word(long long i) const { return n_peers ? sum(i) : acc[i]; }
     __device__ __forceinline__ long long state_word(long long i) const { return n_peers ? sum(state_off + i) : state[i]; }
+    // four words at once: every load is issued before the first one is used (NVLink round trips overlap)
+    __device__ __forceinline__ void acc_words4(const long long* idx, long long* out) const {
+        if (!n_peers) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) out[u] = acc[idx[u]];
+            return;
+        }
+        if (mc) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v[u]) : "l"(mc + idx[u]) : "memory");
+#pragma unroll
+            for (int u = 0; u < 4; ++u) out[u] = (long long)v[u];
+            return;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) out[u] = 0;
+        for (int p0 = 0; p0 < n_peers; p0 += 4) {
+            long long v[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long* base = peers[min(p0 + q, n_peers - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[q][u] = *reinterpret_cast<const volatile long long*>(base + idx[u]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (p0 + q < n_peers)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) out[u] += v[q][u];
+        }
+    }
+    // block until every rank's words of this pass are visible (called by all threads of the CTA)
+    __device__ __forceinline__ void wait_ranks() const {
+        if (flags == nullptr) return;
+        if ((int)threadIdx.x < n_peers) {
+            const unsigned long long want = *seq + 1ull;
+            const long long t0 = clock64();
+            unsigned long long f;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + threadIdx.x) : "memory");
+                if (f < want && clock64() - t0 > (20ll << 30)) __trap();     // ~10 s: a rank died; fail loudly, do not hang
+            } while (f < want);
+        }
+        __syncthreads();
+    }
 };
+
+// Per-pass publish of this rank's partial sums for the exchange above: the acc rows of the runs that are still
+// active and every run's state words are copied into this pass's half of the rank's symmetric-memory buffer (same
+// word offsets as the source, so readers index it like the local buffer); then the last CTA tells every rank (this
+// one included) that the rank's words of pass *seq + 1 are complete by writing that number into the rank's slot of
+// each rank's flag array (release at system scope, after the copies were fenced at system scope).  Two halves
+// alternate: a rank that is one pass ahead writes the other half, and it cannot be two passes ahead because its next
+// k_update waits for this rank's next publish.
+__global__ void __launch_bounds__(256)
+k_exchange_publish(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int AP,
+                   const long long* __restrict__ src, long long n_acc_words, long long* __restrict__ dst,
+                   unsigned long long* const* __restrict__ peer_flags, int n_peers, int my_rank,
+                   unsigned long long* seq, int* counter) {
+    const int run = blockIdx.x;
+    const long long* st = src + n_acc_words + (long long)run * kStateWords;
+    if (threadIdx.x < kStateWords) dst[n_acc_words + (long long)run * kStateWords + threadIdx.x] = st[threadIdx.x];
+    if (st[LEIDA_KM_ST_ACTIVE] != 0) {
+        const long long w0 = (long long)run_crow0[run] * AP, n = (long long)run_k[run] * AP;
+        const longlong2* s2 = reinterpret_cast<const longlong2*>(src + w0);      // AP is a multiple of 8 words
+        longlong2* d2 = reinterpret_cast<longlong2*>(dst + w0);
+        for (long long i = threadIdx.x; i < n / 2; i += blockDim.x) d2[i] = s2[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(counter, 1);
+        if (ticket == n_runs - 1) {
+            *counter = 0;
+            __threadfence_system();
+            const unsigned long long v = *seq + 1ull;
+            *seq = v;
+            for (int p = 0; p < n_peers; ++p)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[p] + my_rank), "l"(v) : "memory");
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int N, int XP,
@@ -468,6 +563,7 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
     __shared__ long long s_cnt[LEIDA_KM_MAX_K];
     const int K = run_k[run], crow0 = run_crow0[run];
     const int AP = XP + 8;
+    red.wait_ranks();
     const bool was_active = st[LEIDA_KM_ST_ACTIVE] != 0;        // block-uniform; only thread 0 writes it, later
     // every thread fetches one cluster's member count (and checks it for emptiness)
     int my_empty = 0;
@@ -506,15 +602,26 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
     __syncthreads();
     const int pv = run_pcol ? run_pcol[run] : -1;      // packed column | slot width << 24 (k_plan)
     if (s_go) {
-        for (int i = threadIdx.x; i < K * XP; i += blockDim.x) {
-            const int k = i / XP, j = i - k * XP;
-            float v = 0.f;
-            if (j < N) {
-                const long long cnt = s_cnt[k];
-                const double sum = (double)red.acc_word((long long)(crow0 + k) * AP + j) * (1.0 / kFracScale);
-                v = (float)(sum / (double)cnt);
+        // four elements per thread and step: their (possibly remote) loads are all in flight together
+        for (int i0 = threadIdx.x; i0 < K * XP; i0 += 4 * blockDim.x) {
+            long long idx[4], w[4];
+            int kk[4], jj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(i0 + u * (int)blockDim.x, K * XP - 1);
+                kk[u] = i / XP;
+                jj[u] = i - kk[u] * XP;
+                idx[u] = (long long)(crow0 + kk[u]) * AP + min(jj[u], N - 1);
             }
-            cent[(long long)(crow0 + k) * XP + j] = v;
+            red.acc_words4(idx, w);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u * (int)blockDim.x < K * XP) {
+                    float v = 0.f;
+                    if (jj[u] < N) v = (float)(((double)w[u] * (1.0 / kFracScale)) / (double)s_cnt[kk[u]]);
+                    cent[(long long)(crow0 + kk[u]) * XP + jj[u]] = v;
+                }
+            }
         }
         __syncthreads();
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -534,6 +641,7 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
             n_active[2] = na;                       // device copy of the last count
             n_active[0] = 0;
             n_active[1] = 0;
+            if (red.flags) *const_cast<unsigned long long*>(red.seq) += 1ull;   // every CTA has read it (all took a ticket)
             if (mailbox) {
                 // device-side copy of the counters (n_active[3] = passes done, n_active[4] = first all-stopped
                 // pass), published to the host as ONE aligned 64-bit store -- a single PCIe write, so the three
@@ -923,20 +1031,36 @@ extern "C" int leida_kmeans_update(int n_runs, const int32_t* run_k, const int32
                                    int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol, void* C1,
                                    void* C2, int32_t* mailbox, leida_stream_t stream) {
     LEIDA_REQUIRE(acc_reduced && state_reduced, "null pointer");
-    ReducedSource red{(const long long*)acc_reduced, (const long long*)state_reduced, nullptr, 0, 0};
+    ReducedSource red{(const long long*)acc_reduced, (const long long*)state_reduced, nullptr, 0, 0, nullptr, nullptr, nullptr};
     return launch_update(n_runs, run_k, run_crow0, N, x_pitch, red, cent, cnorm, state, n_iter, n_active_out, run_pcol,
                          C1, C2, mailbox, stream);
 }
 
 extern "C" int leida_kmeans_update_peers(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N,
                                          int64_t x_pitch, const int64_t* const* peer_bufs, int n_peers,
-                                         int64_t state_offset_words, float* cent, double* cnorm, int64_t* state,
-                                         int n_iter, int32_t* n_active_out, const int32_t* run_pcol, void* C1, void* C2,
-                                         int32_t* mailbox, leida_stream_t stream) {
+                                         const int64_t* multicast_buf, int64_t state_offset_words,
+                                         const uint64_t* flags, const uint64_t* seq, float* cent, double* cnorm,
+                                         int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol,
+                                         void* C1, void* C2, int32_t* mailbox, leida_stream_t stream) {
     LEIDA_REQUIRE(peer_bufs && n_peers >= 1 && n_peers <= 64 && state_offset_words > 0, "peer buffers");
-    ReducedSource red{nullptr, nullptr, (const long long* const*)peer_bufs, n_peers, (long long)state_offset_words};
+    LEIDA_REQUIRE((flags == nullptr) == (seq == nullptr), "flags and seq together");
+    ReducedSource red{nullptr, nullptr, (const long long* const*)peer_bufs, n_peers, (long long)state_offset_words,
+                      (const long long*)multicast_buf, (const unsigned long long*)flags, (const unsigned long long*)seq};
     return launch_update(n_runs, run_k, run_crow0, N, x_pitch, red, cent, cnorm, state, n_iter, n_active_out, run_pcol,
                          C1, C2, mailbox, stream);
+}
+
+extern "C" int leida_kmeans_exchange_publish(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int64_t x_pitch,
+                                             const int64_t* local_words, int64_t n_acc_words, int64_t* exchange_half,
+                                             uint64_t* const* peer_flags, int n_peers, int my_rank, uint64_t* seq,
+                                             int32_t* counter, leida_stream_t stream) {
+    LEIDA_REQUIRE(run_k && run_crow0 && local_words && exchange_half && peer_flags && seq && counter, "null pointer");
+    LEIDA_REQUIRE(n_runs >= 1 && n_runs <= 65535 && x_pitch % 32 == 0 && n_peers >= 1 && n_peers <= 64 &&
+                      my_rank >= 0 && my_rank < n_peers && n_acc_words > 0, "sizes");
+    k_exchange_publish<<<n_runs, 256, 0, (cudaStream_t)stream>>>(
+        n_runs, run_k, run_crow0, (int)x_pitch + 8, (const long long*)local_words, (long long)n_acc_words,
+        (long long*)exchange_half, (unsigned long long* const*)peer_flags, n_peers, my_rank, (unsigned long long*)seq, counter);
+    return check_launch("k_exchange_publish");
 }
 
 extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch, int n_runs,

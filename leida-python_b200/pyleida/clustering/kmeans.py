@@ -274,12 +274,23 @@ class KMeansEngine:
                         nv.ptr(state), stq)
                 timed("apply", f)
             if self.comm.world > 1 and peers is not None:
-                ptrs = peers.publish(red_local)
-                timed("update", lambda: nv.call(
-                    "leida_kmeans_update_peers", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(ptrs),
-                    peers.world, n_acc, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
-                    nv.ptr(run_pcol) if tc else None, nv.ptr(c1) if tc else None, nv.ptr(c2) if tc else None,
-                    mailbox.data_ptr(), stq))
+                f = fast.get(("xchg", stq, peers.half))
+                if f is None:
+                    key = ("xchg", stq, peers.half)
+                    half_ptr, ptrs, mc = peers.next_half()
+                    pub = nv.prepared("leida_kmeans_exchange_publish", R, nv.ptr(run_k), nv.ptr(run_c0), self.XP,
+                                      nv.ptr(red_local), n_acc, half_ptr, nv.ptr(peers._flag_ptrs), peers.world, peers.rank,
+                                      peers.ctr.data_ptr(), nv.ptr(peers.ticket), stq)
+                    upd = nv.prepared("leida_kmeans_update_peers", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP,
+                                      nv.ptr(ptrs), peers.world, mc or None, n_acc, peers.flags_local,
+                                      peers.ctr.data_ptr() + 8, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter),
+                                      nv.ptr(n_active), nv.ptr(run_pcol) if tc else None, nv.ptr(c1) if tc else None,
+                                      nv.ptr(c2) if tc else None, mailbox.data_ptr(), stq)
+                    f = fast[key] = (pub, upd)
+                else:
+                    peers.next_half()
+                timed("publish", f[0])
+                timed("update", f[1])
                 return
             if self.comm.world > 1:
                 red_global.copy_(red_local)
@@ -307,7 +318,7 @@ class KMeansEngine:
         # the host reads to stop, to bound its run-ahead, and to re-pack the tensor-core operands once
         # enough runs have stopped (the active count never increases, so a stale value is a valid
         # upper bound; passes issued after every run has stopped are no-ops).
-        use_graph = tc and centroid_update == "exact" and USE_CUDA_GRAPHS
+        use_graph = tc and centroid_update == "exact" and USE_CUDA_GRAPHS and self.comm.world == 1
         time_assign = profile is not None and (profile.get("*") or "assign" in profile)
         eager_rest = profile is not None and any(k in profile for k in ("*", "recheck", "apply", "update"))
         max_lag = 6

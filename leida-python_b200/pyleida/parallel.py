@@ -101,33 +101,52 @@ def gather_seed_rows(X_local, n_cols, global_rows, row_lo, comm):
 
 
 class PeerExchange:
-    """Double-buffered int64 exchange buffer in symmetric memory (torch.distributed._symmetric_memory):
-    every rank of the node maps every other rank's buffer, so `leida_kmeans_update_peers` can read the
-    partial centroid sums of all ranks in place over NVLink -- the per-pass all-reduce fused into the
-    kernel that consumes it.  One pass = publish(local words) [device copy into this pass's
-    half + a cross-rank barrier on the stream] -> kernel reads `ptrs()`.  Two halves alternate, so a rank
-    that is one pass ahead never overwrites what a slower rank is still reading: it cannot be two passes
-    ahead because every pass has a barrier.
+    """The per-pass exchange of the k-means partial sums over symmetric memory (torch.distributed._symmetric_memory;
+    SURVEY 8e), fused into the kernel that consumes it.  Every rank owns a buffer of two halves (+ one flag word per
+    rank) that every other rank of the node maps.  One pass:
+        leida_kmeans_exchange_publish  copies the rank's int64 words of the still-active runs into this pass's half
+                                       and raises the rank's flag on every rank;
+        leida_kmeans_update_peers      waits for all flags, then reads every word as the sum over ranks -- one
+                                       multimem.ld_reduce through the NVSwitch multicast mapping when the group has
+                                       one, else one load per rank over NVLink.
+    No NCCL launch, no host involvement, no separate barrier kernel; the payload shrinks with the number of active
+    runs.  Two halves alternate, so a rank that is one pass ahead never overwrites what a slower rank is still
+    reading: it cannot be two passes ahead because its next update waits for the slower rank's next publish.
 
-    get() is collective.  It returns None on every rank if any rank cannot set the mapping up (no
-    symmetric-memory support, ranks on different nodes) or if the mode says NCCL; the caller then uses the
-    NCCL all-reduce.  LEIDA_EXCHANGE = peer | nccl | auto (default).  auto = peer reads for 2 ranks, NCCL
-    for more: in-place reads move (world-1) x the payload per rank and need a full cross-rank barrier per
-    pass, NCCL moves ~2x the payload.  Measured on B200 / NVSwitch (config 2 per GPU, ms per step):
-    2 GPUs 82.0 peer vs 85.6 NCCL; 8 GPUs 87.9 peer vs 81.5 NCCL (also when only the late passes with few
-    active runs use the peer path: 87.8).  Buffers are cached per (group, device) and reused by later engines."""
+    get() is collective.  It returns None on every rank if any rank cannot set the mapping up (no symmetric-memory
+    support, ranks on different nodes) or if LEIDA_EXCHANGE=nccl; the caller then uses copy + ncclAllReduce.
+    LEIDA_EXCHANGE = auto (default: symmetric memory when available) | peer (same, loads per rank even when multicast
+    exists) | nccl.  Buffers are cached per (group, device) and reused by later engines."""
     _cache = {}
+    FLAG_WORDS = 64
 
-    def __init__(self, words, dev, group):
+    def __init__(self, words, dev, group, use_multicast=True):
         import torch
         import torch.distributed._symmetric_memory as symm
         self.words = int(words)
-        self.buf = symm.empty(2 * self.words, dtype=torch.int64, device=dev)
+        self.buf = symm.empty(2 * self.words + self.FLAG_WORDS, dtype=torch.int64, device=dev)
+        self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
         self.world = int(self.hdl.world_size)
+        self.rank = int(self.hdl.rank)
         base = [int(p) for p in self.hdl.buffer_ptrs]
         self._ptrs = [torch.tensor([b + h * self.words * 8 for b in base], dtype=torch.int64, device=dev) for h in (0, 1)]
+        self._flag_ptrs = torch.tensor([b + 2 * self.words * 8 for b in base], dtype=torch.int64, device=dev)
+        self.flags_local = base[self.rank] + 2 * self.words * 8
+        mc = 0
+        if use_multicast:
+            try:
+                mc = int(self.hdl.multicast_ptr or 0)   # 0 / None: the group has no NVSwitch multicast mapping
+            except Exception:                           # noqa: BLE001 - no multicast: loads per rank
+                mc = 0
+        self.multicast = mc
+        # device-resident pass counters: [0] passes published, [1] passes consumed (uint64), and the publish ticket
+        self.ctr = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
         self.half = 0
+        torch.cuda.synchronize(dev)
+        self.hdl.barrier(channel=0)                     # every rank's flags are zero before anyone publishes
+        torch.cuda.synchronize(dev)
 
     @classmethod
     def get(cls, comm, words, dev):
@@ -141,27 +160,28 @@ class PeerExchange:
         ex = cls._cache.get(key)
         ok = 1
         mode = os.environ.get("LEIDA_EXCHANGE", "auto")
-        if mode == "nccl" or (mode != "peer" and comm.world > 2):
+        if mode == "nccl":
             ok = 0
         elif ex is None or ex.words < words:
             try:
-                ex = cls(max(int(words), 1 << 19), dev, group)
+                ex = cls(max(int(words), 1 << 19), dev, group, use_multicast=(mode != "peer"))
             except Exception as e:                      # noqa: BLE001 - any failure means "use NCCL"
                 import warnings
-                warnings.warn(f"peer-memory exchange unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce")
+                warnings.warn(f"symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce")
                 ex, ok = None, 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        flag = torch.tensor([ok, 1 if (ex is not None and ex.multicast) else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
-        if int(flag.item()) == 0:
+        if int(flag[0].item()) == 0:
             return None
+        if int(flag[1].item()) == 0:
+            ex.multicast = 0                            # all ranks read the same way
         cls._cache[key] = ex
         return ex
 
-    def publish(self, local_words):
-        """Copy this rank's words into the current half and order it against every rank (on the current
-        stream).  Returns the device array of per-rank pointers to that half."""
+    def next_half(self):
+        """(pointer to this rank's half of the pass, device array of every rank's pointer to that half, multicast
+        address of the half or 0); alternates."""
         h = self.half
         self.half ^= 1
-        self.buf[h * self.words: h * self.words + local_words.numel()].copy_(local_words)
-        self.hdl.barrier(channel=0)
-        return self._ptrs[h]
+        off = h * self.words * 8
+        return self.buf.data_ptr() + off, self._ptrs[h], (self.multicast + off) if self.multicast else 0
