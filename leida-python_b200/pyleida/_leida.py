@@ -108,10 +108,10 @@ class Leida:
         """_leida.py:111-192.  K range and n_init are arguments here (the reference hard-codes
         2..20 and 15, :156-157 / _clustering.py:250); stats=True runs the permutation tests on the occupancy and
         dwell-time tables like the reference (_leida.py:336-342; on the GPU, stats/_stats.py) when there are at least
-        two conditions with two rows each, on single-GPU runs; save_results=True writes the reference's
+        two conditions with two rows each (on multi-GPU runs the per-subject tables are gathered first); save_results=True writes the reference's
         'LEiDA_results' folder layout (results_io.py) and, like the reference, refuses to overwrite it.  scores=True
         fills the Dunn / silhouette / Davies-Bouldin columns of the performance table like the reference
-        (they are not part of the benchmarked hot path; single-GPU only)."""
+        (they are not part of the benchmarked hot path; multi-GPU runs gather the scored 30 000-row sample)."""
         if TR is not None and not isinstance(TR, (int, float)):
             raise TypeError("'TR' must be 'None', and integer or a floating number!")
         if not isinstance(paired_tests, bool):
@@ -241,13 +241,11 @@ class Leida:
         occ, runs, trans = pinned["occ"].numpy(), pinned["runs"].numpy(), pinned["trans"].numpy()
         self.d2h_bytes += labels.nbytes + labels_t.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
         sc = None
-        if scores and comm.world == 1:                     # Dunn / silhouette / Davies-Bouldin (_clustering.py:331-339)
+        if scores:                                         # Dunn / silhouette / Davies-Bouldin (_clustering.py:331-339)
             from .clustering.kmeans import score_sample, sweep_runs
             from .clustering.scores import clustering_scores
             sc = clustering_scores(res.engine, res.labels, ks, [res.models[k]._centers_exact() for k in ks],
-                                   score_sample(res.engine.M, sweep_runs.last_sample))
-        elif scores:
-            warnings.warn("clustering scores are computed on single-GPU runs only; reporting NaN")
+                                   score_sample(res.engine.m_global, sweep_runs.last_sample, comm))
         predictions = pd.DataFrame({"subject_id": pd.Series(sub_list, dtype=object),
                                     "condition": pd.Series(cond_list, dtype=object)})
         models, perf = {}, []
@@ -286,24 +284,34 @@ class Leida:
         if not stats:
             return
         comm = self._comm if self._comm is not None else Comm()
+        occ, dwl = self._dynamics_.occupancies, self._dynamics_.dwell_times
         if comm.world > 1:
-            warnings.warn("the statistics stage needs every subject on one GPU; skipped on multi-GPU runs")
-            return
-        first = self._dynamics_.occupancies[f"k_{self._K_min_}"]
+            # the tables are one row per (subject, condition): small.  Every rank receives every rank's rows, puts them
+            # in the reference's row order (sorted condition, then sorted subject: _dynamics_metrics.py:180-182) and runs
+            # the same tests, so Leida.stats() answers on every rank.
+            import pandas as pd
+            parts = comm.all_gather_object({m: {k: t[k] for k in t.keys()} for m, t in (("occupancies", occ), ("dwell_times", dwl))})
+
+            def whole(metric, k):
+                df = pd.concat([p[metric][k] for p in parts], ignore_index=True)
+                return df.sort_values(["condition", "subject_id"], kind="stable").reset_index(drop=True)
+            occ = {k: whole("occupancies", k) for k in occ.keys()}
+            dwl = {k: whole("dwell_times", k) for k in dwl.keys()}
+        first = occ[f"k_{self._K_min_}"]
         sizes = first.groupby("condition").size()
         if len(sizes) < 2 or int(sizes.min()) < 2:
             return                                   # nothing to compare (the reference would fail inside scipy here)
         if paired_tests and len(set(sizes.tolist())) != 1:
             raise ValueError("paired_tests=True needs the same number of rows in every condition")
         from .stats import _compute_stats
-        tables = {"occupancies": self._dynamics_.occupancies, "dwell_times": self._dynamics_.dwell_times}
+        tables = {"occupancies": occ, "dwell_times": dwl}
         self._dynamics_["stats"] = _compute_stats(tables, paired_tests=paired_tests, n_perm=n_perm, save_results=False,
                                                   random_state=random_state if isinstance(random_state, int) else None)
 
     def stats(self, k=2, metric="occupancies"):
         """Results of the statistical analysis for the K partition (_leida.py:475-500)."""
         if self._dynamics_.get("stats") is None:
-            raise Exception("the statistics stage was not run (stats=False, a single condition, or a multi-GPU run)")
+            raise Exception("the statistics stage was not run (stats=False or a single condition)")
         return self._dynamics_["stats"][metric][f"k_{k}"]
 
     # ------------------------------------------------------------------------------------------

@@ -597,14 +597,21 @@ class KMeansLeida:
         return eng.predict(self.cluster_centers_).cpu().numpy().astype(np.int64)
 
 
-def score_sample(M, drawn=None):
+def score_sample(M, drawn=None, comm=None):
     """Rows scored by Dunn / silhouette: all of them up to 30 000, else the reference's 30 000-row random
-    sub-sample (clustering/_clustering.py:318-320) -- `drawn` when the draw was already made."""
+    sub-sample (clustering/_clustering.py:318-320) -- `drawn` when the draw was already made.  With several ranks the
+    draw is rank 0's (every process has its own global RNG)."""
     if M <= 30_000:
         # the reference's two tests (N_samples>30_000 to draw, N_samples<30_000 to use everything) leave
         # M == 30 000 undefined (NameError); everything is scored here
         return None
-    return drawn if drawn is not None else np.random.choice(np.arange(M), size=30_000, replace=False)
+    if drawn is not None:
+        return drawn
+    multi = comm is not None and comm.world > 1
+    idx = np.zeros(30_000, dtype=np.int64)
+    if not multi or comm.rank == 0:
+        idx[:] = np.random.choice(np.arange(M), size=30_000, replace=False)
+    return comm.bcast0_int64(idx) if multi else idx
 
 
 def sweep_runs(M, K_min, K_max, n_init, random_state=None, init_indices=None, comm=None):
@@ -703,7 +710,7 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
     eigens_dataset: DataFrame with 'subject_id', 'condition' and one column per ROI (the reference's
     input), or a (metadata DataFrame, KMeansEngine) pair through `engine` to reuse device data.
     scores=True computes the Dunn / silhouette / Davies-Bouldin columns (:331-339) on the GPU
-    (clustering/scores.py; single-GPU engines only, NaN otherwise); `plot` is accepted and ignored.
+    (clustering/scores.py; row-sharded engines gather the scored sample); `plot` is accepted and ignored.
     init_indices: optional {k: [idx_r ...]} replacing the legacy-RNG draws.
     """
     import pandas as pd
@@ -718,14 +725,12 @@ def identify_states(eigens_dataset, K_min=2, K_max=20, n_init=15, random_state=N
     by_k = select_models(engine, res, plan, n_init)
     ks = list(range(K_min, K_max + 1))
     sc = None
-    if scores and engine.comm.world == 1:
+    if scores:
         from .scores import clustering_scores
         torch = engine.torch
         sc = clustering_scores(engine, torch.stack([by_k[k].labels_device_ for k in ks]), ks,
                                [by_k[k]._centers_exact() for k in ks],
-                               score_sample(engine.M, sweep_runs.last_sample))
-    elif scores:
-        warnings.warn("clustering scores are computed on single-GPU engines only; reporting NaN")
+                               score_sample(engine.m_global, sweep_runs.last_sample, engine.comm))
     models, perf = {}, []
     for c, k in enumerate(ks):
         km = by_k[k]

@@ -11,12 +11,19 @@ from .. import _native as nv
 
 
 def clustering_scores(engine, labels, ks, centroids64, sample_idx=None):
-    """engine: KMeansEngine (rows on the device); labels: CUDA int32 (n_cols, M) final (remapped)
+    """engine: KMeansEngine (rows on the device); labels: CUDA int32 (n_cols, M_local) final (remapped)
     labels; ks[c] = K of column c; centroids64[c]: (K, N) float64 exact member means of column c;
-    sample_idx: rows scored by Dunn / silhouette (None = all).  Davies-Bouldin always uses every row,
-    like the reference.  Returns dict of three float64 arrays (n_cols)."""
+    sample_idx: GLOBAL indices of the rows scored by Dunn / silhouette (None = all).  Davies-Bouldin always uses
+    every row, like the reference.  Returns dict of three float64 arrays (n_cols).
+
+    Row-sharded engines (several GPUs): the scored rows -- at most the reference's 30 000-row sample -- and their
+    labels are gathered on every rank (each row is owned by one rank, the others add zeros), so Dunn and the
+    silhouette are computed from exactly the single-GPU inputs; Davies-Bouldin adds the ranks' int64 distance sums
+    and member counts.  Every rank returns the same values."""
     torch = nv.require_cuda()
+    from ..parallel import gather_seed_rows
     dev = engine.X.device
+    comm = engine.comm
     n_cols = len(ks)
     col_k = np.asarray(ks, dtype=np.int32)
     col0 = np.zeros(n_cols, dtype=np.int32)
@@ -24,8 +31,23 @@ def clustering_scores(engine, labels, ks, centroids64, sample_idx=None):
     total = int(col_k.sum())
     labels = labels.to(torch.int32).contiguous()
     M, N, XP = engine.M, engine.N, engine.XP
-    n = M if sample_idx is None else len(sample_idx)
-    sel = None if sample_idx is None else torch.from_numpy(np.ascontiguousarray(sample_idx, dtype=np.int64)).to(dev)
+    if comm.world > 1:
+        idx = np.arange(engine.m_global, dtype=np.int64) if sample_idx is None else np.asarray(sample_idx, dtype=np.int64)
+        if len(idx) > 60_000:
+            raise ValueError("scoring more than 60 000 rows on a sharded engine is not supported (the reference samples 30 000)")
+        Xs = gather_seed_rows(engine.X, N, idx, engine.row_lo, comm)                 # (n, XP) on every rank
+        gi = torch.from_numpy(idx).to(dev)
+        mine = (gi >= engine.row_lo) & (gi < engine.row_lo + M)
+        labs = torch.zeros((n_cols, len(idx)), dtype=torch.int32, device=dev)
+        if bool(mine.any()):
+            labs[:, mine] = labels[:, gi[mine] - engine.row_lo]
+        comm.all_reduce_sum_(labs)
+        n, sel, lab_s, pitch_s = len(idx), None, labs, len(idx)
+    else:
+        Xs = engine.X
+        n = M if sample_idx is None else len(sample_idx)
+        sel = None if sample_idx is None else torch.from_numpy(np.ascontiguousarray(sample_idx, dtype=np.int64)).to(dev)
+        lab_s, pitch_s = labels, M
     d_col0, d_colk = torch.from_numpy(col0).to(dev), torch.from_numpy(col_k).to(dev)
     xs = torch.empty((n, XP), dtype=torch.float32, device=dev)
     G = torch.empty((total, XP), dtype=torch.int64, device=dev)
@@ -33,25 +55,35 @@ def clustering_scores(engine, labels, ks, centroids64, sample_idx=None):
     sil = torch.empty(n_cols, dtype=torch.int64, device=dev)
     mn = torch.empty(n_cols, dtype=torch.int32, device=dev)
     mx = torch.empty(n_cols, dtype=torch.int32, device=dev)
-    nv.call("leida_scores_cosine", nv.ptr(engine.X), XP, N, nv.ptr(sel), n, nv.ptr(labels), M, n_cols, nv.ptr(d_col0),
+    nv.call("leida_scores_cosine", nv.ptr(Xs), XP, N, nv.ptr(sel), n, nv.ptr(lab_s), pitch_s, n_cols, nv.ptr(d_col0),
             nv.ptr(d_colk), total, nv.ptr(xs), nv.ptr(G), nv.ptr(cnt), nv.ptr(sil), nv.ptr(mn), nv.ptr(mx), nv.stream())
-    cents = torch.from_numpy(np.ascontiguousarray(np.vstack(centroids64), dtype=np.float64)).to(dev)
-    dsum = torch.empty(total, dtype=torch.int64, device=dev)
-    nv.call("leida_scores_db", nv.ptr(engine.X), XP, N, M, nv.ptr(labels), M, n_cols, nv.ptr(d_col0), nv.ptr(cents), total,
-            nv.ptr(dsum), nv.stream())
+    # Davies-Bouldin is a ratio of Euclidean distances: evaluated in the engine's (power-of-two scaled) units
+    cen_all = [np.asarray(c, dtype=np.float64) / engine.scale for c in centroids64]
+    cents = torch.from_numpy(np.ascontiguousarray(np.vstack(cen_all), dtype=np.float64)).to(dev)
+    dsum = torch.zeros(total, dtype=torch.int64, device=dev)
+    if M > 0:
+        nv.call("leida_scores_db", nv.ptr(engine.X), XP, N, M, nv.ptr(labels), M, n_cols, nv.ptr(d_col0), nv.ptr(cents), total,
+                nv.ptr(dsum), nv.stream())
+    counts_all = torch.zeros(total, dtype=torch.int64, device=dev)
+    for c in range(n_cols):
+        K = int(col_k[c])
+        counts_all[col0[c]:col0[c] + K] = torch.bincount(labels[c].long(), minlength=K)[:K]
+    if comm.world > 1:
+        comm.all_reduce_sum_(dsum)
+        comm.all_reduce_sum_(counts_all)
     sil_h = sil.cpu().numpy().astype(np.float64) * 2.0 ** -40 / n
     mn_h = mn.cpu().numpy().view(np.float32).astype(np.float64)
     mx_h = mx.cpu().numpy().view(np.float32).astype(np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
         dunn = mn_h / mx_h                                       # np.min(deltas) / np.max(big_deltas)   (:958)
     dsum_h = dsum.cpu().numpy().astype(np.float64) * 2.0 ** -40
+    counts_h = counts_all.cpu().numpy().astype(np.float64)
     db = np.empty(n_cols)
     for c in range(n_cols):
         K = int(col_k[c])
-        counts = torch.bincount(labels[c].long(), minlength=K)[:K].cpu().numpy().astype(np.float64)
         with np.errstate(divide="ignore", invalid="ignore"):
-            intra = dsum_h[col0[c]:col0[c] + K] / counts           # mean distance of the members to their centroid
-        cen = np.asarray(centroids64[c], dtype=np.float64)
+            intra = dsum_h[col0[c]:col0[c] + K] / counts_h[col0[c]:col0[c] + K]   # mean distance of the members to their centroid
+        cen = cen_all[c]
         diff = cen[:, None, :] - cen[None, :, :]
         cd = np.sqrt((diff * diff).sum(-1))                      # pairwise_distances(centroids)
         if np.allclose(intra, 0) or np.allclose(cd, 0):

@@ -66,6 +66,14 @@ class Comm:
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
+    def all_gather_object(self, obj):
+        """Gather one picklable object from every rank -> list (rank order)."""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self._dist.all_gather_object(out, obj, group=self.group)
+        return out
+
     def all_gather_int(self, value):
         """Gather one python int from every rank -> list."""
         import torch

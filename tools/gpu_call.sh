@@ -2,6 +2,7 @@
 # Round-2 GPU session script (run under gpurun from the repo root).  Usage: tools/gpu_call.sh <tag> <stage...>
 set -u
 TAG=$1; shift
+NG=${NG:-2}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 for stage in "$@"; do
@@ -14,6 +15,8 @@ for stage in "$@"; do
     bench2)    timeout 600 python bench.py --config config2 --steps 5 --warmup 3 --no-cpu > $OUT/bench_config2.json 2> $OUT/bench_config2.err; echo "bench2 rc=$?" ;;
     ref)       timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?" ;;
     ncu_list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-secondary > $OUT/ncu_list.log 2>&1; echo "ncu_list rc=$?" ;;
+    mgpu)      for x in auto peer nccl; do LEIDA_EXCHANGE=$x timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py > $OUT/mgpu_check_${NG}gpu_$x.log 2>&1; echo "mgpu $x rc=$?"; grep "world=" $OUT/mgpu_check_${NG}gpu_$x.log; done ;;
+    mbench)    for x in ${XCHG:-auto nccl}; do LEIDA_EXCHANGE=$x timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --steps 3 --warmup 2 > $OUT/bench_${NG}gpu_$x.json 2> $OUT/bench_${NG}gpu_$x.err; echo "mbench $x rc=$?"; done ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
