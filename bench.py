@@ -393,6 +393,8 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
     for _ in range(warmup):
         step_device()                                  # result dropped at once: the timed steps reuse its memory
     profile = {"*": True}
+    if os.environ.get("LEIDA_BENCH_DUMP"):
+        profile["trace_active"] = True
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -408,7 +410,7 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
         res = step_device(profile)
         graph_launches += res.batch.graph_launches
         b = res.batch
-        stats = dict(run_passes=b.total_passes(), lockstep=b.lockstep_passes, n_runs=len(b._ks),
+        stats = dict(run_passes=b.total_passes(), lockstep=b.lockstep_passes, n_runs=len(b._ks), exchange=b.exchange,
                      sum_k_passes=float(sum(b.k(i) * b.passes(i) for i in range(len(b._ks)))),
                      rechecked=b.rechecked_total, changed=b.changed_total)
         del b
@@ -438,7 +440,14 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
 
     # roofline of the dominant kernel + the other kernels of the pass loop, from the event pairs recorded inside the
     # timed region (this rank)
+    active_trace = profile.pop("active_after_pass", None)
+    profile.pop("trace_active", None)
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in profile.items() if k != "*"}
+    if os.environ.get("LEIDA_BENCH_DUMP") and rank == 0:
+        # per-launch durations of the LAST timed step, kernel by kernel (profiles/: where the passes spend their time)
+        per = {k: [round(a.elapsed_time(b), 4) for a, b in v[-(len(v) // steps):]] for k, v in profile.items() if k != "*"}
+        with open(os.environ["LEIDA_BENCH_DUMP"], "w") as f:
+            json.dump({"config": key, "n_gpus": world, "per_launch_ms": per, "active_after_pass": active_trace}, f)
     kernel_n = {k: len(v) for k, v in profile.items() if k != "*"}
     assign_ms = kernel_ms.get("assign", 0.0)
     n_assign = kernel_n.get("assign", 0)
@@ -533,7 +542,8 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
     run_stats = {"subjects_on_rank0": hi - lo, "rows_total": M_global, "kmeans_run_passes_per_step": run_passes,
                  "lockstep_passes_per_step": stats["lockstep"], "fp64_rechecks_per_step": rechecked,
                  "label_changes_per_step": changed, "per_step_ms": [round(v, 2) for v in per_step_ms],
-                 "input_generation_s": round(t_gen, 1), "parallelism": f"subjects sharded over {world} GPU(s)"}
+                 "input_generation_s": round(t_gen, 1), "parallelism": f"subjects sharded over {world} GPU(s)",
+                 "exchange": stats["exchange"]}
     return dict(value=value, ms_per_step=ms / steps, launches=int(ln.item()), roofline=roofline, e2e=e2e, parity=parity,
                 clocks=clocks, run_stats=run_stats, stats=stats)
 

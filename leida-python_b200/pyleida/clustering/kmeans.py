@@ -328,6 +328,7 @@ class KMeansEngine:
         grid_bound = [R]        # upper bound of the packed-run count, sizes the apply grid (eager launches only)
         issued = 0
         graphs = None
+        act_hist = torch.zeros(2048, dtype=torch.int32, device=dev) if (profile is not None and profile.get("trace_active")) else None
         while True:
             if tc and mb_read()[2] == 0 and 0 < active_bound <= 0.9 * packed_bound:
                 tc_plan()                              # re-pack: only the runs still active keep tensor-core columns
@@ -346,6 +347,8 @@ class KMeansEngine:
                 graphs[1].replay()
             else:
                 graphs[0].replay()
+            if act_hist is not None and issued < act_hist.numel():
+                act_hist[issued:issued + 1].copy_(n_active[2:3])       # runs still active after this pass (profiling only)
             issued += 1
             while issued - mb_read()[1] > max_lag:
                 pass
@@ -361,6 +364,8 @@ class KMeansEngine:
             if issued > n_iter + 2 + 2 * max_lag:
                 raise nv.LeidaCudaError("k-means did not terminate (internal error)")
         passes = issued
+        if act_hist is not None:
+            profile["active_after_pass"] = act_hist[:min(issued, 2048)].cpu().tolist()
         launches = issued * launches_per_pass
         graph_launches = (issued - 1) * launches_per_pass if graphs is not None else 0   # not seen by the C-side counter
         timed("distortion", lambda: nv.call(
@@ -396,6 +401,8 @@ class KMeansEngine:
         out.rechecked_total = int(st_host[:, nv.ST_RECHECK_TOTAL].sum())
         out.changed_total = int(st_host[:, nv.ST_CHANGED_TOTAL].sum())
         out.assign = assign
+        out.exchange = ("none" if self.comm.world == 1 else "nccl all-reduce" if peers is None else
+                        "symmetric memory, multimem.ld_reduce" if peers.multicast else "symmetric memory, loads per rank")
         out.graph_launches = graph_launches
         out._acc = acc_red                    # exact fixed-point member sums (device), for centers_exact()
         return out
