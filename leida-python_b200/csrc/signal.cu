@@ -5,6 +5,7 @@
 //   * rank-2 closed-form leading eigenvector       _signal_tools.py:137-224 (dFC never materialised)
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace leida {
 
@@ -12,23 +13,47 @@ namespace leida {
 // FFT machinery.  Stockham autosort, decimation in frequency, one CTA per transform, data in shared
 // memory as double2.  Twiddles tw[k] = exp(-2 pi i k / n) live in global memory (L1-resident).
 // ------------------------------------------------------------------------------------------------
+// A pass is a Stockham step of radix r1*r2: r2 == 1 is a plain radix (2, 3, 4, 5 or an odd prime up to 31); r2 > 1 is
+// a composite radix whose r1*r2-point butterfly is done in registers (Cooley-Tukey r1 x r2 with internal twiddles), so
+// T = 1200 = (5*3) * 5 * (4*4) needs three trips through shared memory instead of five.
 struct FftPlan {
     int n;
     int nfac;
-    int radix[20];
+    unsigned char r1[20];
+    unsigned char r2[20];
 };
 
 static bool make_plan(int n, FftPlan& p) {
     p.n = n;
     p.nfac = 0;
+    int small[32], ns = 0, big[32], nbig = 0;
     int m = n;
-    while (m % 4 == 0) { p.radix[p.nfac++] = 4; m /= 4; }
-    while (m % 2 == 0) { p.radix[p.nfac++] = 2; m /= 2; }
-    while (m % 3 == 0) { p.radix[p.nfac++] = 3; m /= 3; }
-    while (m % 5 == 0) { p.radix[p.nfac++] = 5; m /= 5; }
+    while (m % 5 == 0) { small[ns++] = 5; m /= 5; }
+    while (m % 4 == 0) { small[ns++] = 4; m /= 4; }
+    while (m % 3 == 0) { small[ns++] = 3; m /= 3; }
+    while (m % 2 == 0) { small[ns++] = 2; m /= 2; }
     for (int f = 7; f <= 31 && m > 1; f += 2)
-        while (m % f == 0) { p.radix[p.nfac++] = f; m /= f; }
-    return m == 1;
+        while (m % f == 0) { big[nbig++] = f; m /= f; }
+    if (m != 1) return false;
+    // pair the small factors (descending) greedily: the largest remaining factor takes the largest partner that keeps
+    // the product <= 16 (the register budget of a composite butterfly)
+    for (int i = 0; i < ns; ++i)
+        for (int j = i + 1; j < ns; ++j)
+            if (small[j] > small[i]) { int t = small[i]; small[i] = small[j]; small[j] = t; }
+    bool used[32] = {false};
+    for (int i = 0; i < ns; ++i) {
+        if (used[i]) continue;
+        used[i] = true;
+        int partner = -1;
+        for (int j = i + 1; j < ns; ++j)
+            if (!used[j] && small[i] * small[j] <= 16) { partner = j; break; }
+        p.r1[p.nfac] = (unsigned char)small[i];
+        p.r2[p.nfac] = 1;
+        if (partner >= 0) { used[partner] = true; p.r2[p.nfac] = (unsigned char)small[partner]; }
+        ++p.nfac;
+    }
+    for (int i = 0; i < nbig; ++i) { p.r1[p.nfac] = (unsigned char)big[i]; p.r2[p.nfac] = 1; ++p.nfac; }
+    return true;
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -88,57 +113,105 @@ __device__ __forceinline__ void butterfly<5>(double2* v) {
     v[3] = c_pi(m2, n2);
 }
 
-// One Stockham pass of radix R: n/R butterflies spread over the CTA.
-template <int R>
+// r1*r2-point DFT in registers, natural order in and out: X[b + R1 c] = sum_a w_R2^{ac} w_R^{ab} sum_d w_R1^{db} x[a + R2 d].
+// w_R^m = tw[m * wstep] (wstep = n / R; R divides n).
+template <int R1, int R2>
+__device__ __forceinline__ void butterfly2(double2* v, const double2* __restrict__ tw, int wstep) {
+    constexpr int R = R1 * R2;
+    double2 y[R];
+#pragma unroll
+    for (int a = 0; a < R2; ++a) {
+        double2 t[R1];
+#pragma unroll
+        for (int d = 0; d < R1; ++d) t[d] = v[a + R2 * d];
+        butterfly<R1>(t);
+#pragma unroll
+        for (int b = 0; b < R1; ++b) y[a * R1 + b] = (a * b) ? cmul(t[b], __ldg(&tw[(a * b) * wstep])) : t[b];
+    }
+#pragma unroll
+    for (int b = 0; b < R1; ++b) {
+        double2 t[R2];
+#pragma unroll
+        for (int a = 0; a < R2; ++a) t[a] = y[a * R1 + b];
+        butterfly<R2>(t);
+#pragma unroll
+        for (int c = 0; c < R2; ++c) v[b + R1 * c] = t[c];
+    }
+}
+
+// One Stockham pass of radix R1*R2 over `batch` transforms held side by side in shared memory (transform i at
+// in + i * stride): batch * n/R butterflies spread over the CTA.
+template <int R1, int R2>
 __device__ __forceinline__ void fft_pass(const double2* __restrict__ in, double2* __restrict__ out,
-                                         const double2* __restrict__ tw, int n, int len, int s) {
+                                         const double2* __restrict__ tw, int n, int len, int s, int batch, int stride) {
+    constexpr int R = R1 * R2;
     const int m = len / R, nb = n / R, tstep = n / len;
-    for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-        const int p = idx / s, q = idx - p * s;
+    for (int idx = threadIdx.x; idx < nb * batch; idx += blockDim.x) {
+        const int bi = idx / nb, i = idx - bi * nb;
+        const int p = i / s, q = i - p * s;
+        const double2* ib = in + (size_t)bi * stride;
         double2 v[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) v[k] = in[q + s * (p + k * m)];
-        butterfly<R>(v);
-        double2* o = out + q + s * (R * p);
+        for (int k = 0; k < R; ++k) v[k] = ib[q + s * (p + k * m)];
+        if constexpr (R2 == 1) butterfly<R1>(v);
+        else butterfly2<R1, R2>(v, tw, n / R);
+        double2* o = out + (size_t)bi * stride + q + s * (R * p);
         o[0] = v[0];
+        if (p == 0) {
 #pragma unroll
-        for (int j = 1; j < R; ++j) o[s * j] = cmul(v[j], __ldg(&tw[p * j * tstep]));
+            for (int j = 1; j < R; ++j) o[s * j] = v[j];
+        } else {
+#pragma unroll
+            for (int j = 1; j < R; ++j) o[s * j] = cmul(v[j], __ldg(&tw[p * j * tstep]));
+        }
     }
 }
 
 // Generic odd prime radix (7..31): O(r^2) butterfly from the twiddle table.
 __device__ __noinline__ void fft_pass_generic(const double2* __restrict__ in, double2* __restrict__ out,
-                                              const double2* __restrict__ tw, int n, int len, int s, int r) {
+                                              const double2* __restrict__ tw, int n, int len, int s, int r, int batch,
+                                              int stride) {
     const int m = len / r, nb = n / r, tstep = n / len, rstep = n / r;
-    for (int idx = threadIdx.x; idx < nb; idx += blockDim.x) {
-        const int p = idx / s, q = idx - p * s;
+    for (int idx = threadIdx.x; idx < nb * batch; idx += blockDim.x) {
+        const int bi = idx / nb, i = idx - bi * nb;
+        const int p = i / s, q = i - p * s;
+        const double2* ib = in + (size_t)bi * stride;
+        double2* ob = out + (size_t)bi * stride;
         double2 v[31];
-        for (int k = 0; k < r; ++k) v[k] = in[q + s * (p + k * m)];
+        for (int k = 0; k < r; ++k) v[k] = ib[q + s * (p + k * m)];
         for (int j = 0; j < r; ++j) {
             double2 acc = v[0];
             for (int k = 1; k < r; ++k) acc = cadd(acc, cmul(v[k], __ldg(&tw[((j * k) % r) * rstep])));
-            out[q + s * (r * p + j)] = cmul(acc, __ldg(&tw[p * j * tstep]));
+            ob[q + s * (r * p + j)] = cmul(acc, __ldg(&tw[p * j * tstep]));
         }
     }
 }
 
-// Forward DFT of plan.n points held in `src`; on return `src` points at the result.
+// Forward DFT of `batch` transforms of plan.n points (transform i at src + i * stride, scratch at dst + i * stride);
+// on return `src` points at the results.
 __device__ __forceinline__ void fft_forward(double2*& src, double2*& dst, const double2* __restrict__ tw,
-                                            const FftPlan& plan) {
+                                            const FftPlan& plan, int batch = 1, int stride = 0) {
     int len = plan.n, s = 1;
     for (int f = 0; f < plan.nfac; ++f) {
-        const int r = plan.radix[f];
-        switch (r) {
-            case 4: fft_pass<4>(src, dst, tw, plan.n, len, s); break;
-            case 2: fft_pass<2>(src, dst, tw, plan.n, len, s); break;
-            case 3: fft_pass<3>(src, dst, tw, plan.n, len, s); break;
-            case 5: fft_pass<5>(src, dst, tw, plan.n, len, s); break;
-            default: fft_pass_generic(src, dst, tw, plan.n, len, s, r); break;
+        const int r1 = plan.r1[f], r2 = plan.r2[f];
+        switch (r1 * 8 + r2) {
+            case 4 * 8 + 4: fft_pass<4, 4>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 5 * 8 + 3: fft_pass<5, 3>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 5 * 8 + 2: fft_pass<5, 2>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 4 * 8 + 3: fft_pass<4, 3>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 4 * 8 + 2: fft_pass<4, 2>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 3 * 8 + 3: fft_pass<3, 3>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 3 * 8 + 2: fft_pass<3, 2>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 5 * 8 + 1: fft_pass<5, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 4 * 8 + 1: fft_pass<4, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 3 * 8 + 1: fft_pass<3, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 2 * 8 + 1: fft_pass<2, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            default: fft_pass_generic(src, dst, tw, plan.n, len, s, r1, batch, stride); break;
         }
         __syncthreads();
         double2* t = src; src = dst; dst = t;
-        len /= r;
-        s *= r;
+        len /= r1 * r2;
+        s *= r1 * r2;
     }
 }
 
@@ -213,44 +286,83 @@ __global__ void k_bluestein_bhat(const double2* __restrict__ chirp, const double
     for (int n = threadIdx.x; n < L; n += blockDim.x) bhat[n] = a[n];
 }
 
-// Hilbert phase of two real series per transform: z = x1 + i x2; A(z) = ifft(h fft(z)) =
-// (x1 - H x2) + i (x2 + H x1)  =>  H x1 = Im A - x2,  H x2 = x1 - Re A;  theta = atan2(H x, x).
-template <bool BLUESTEIN>
-__global__ void k_hilbert_phase(const double* __restrict__ x, long long n_series, int T, long long x_pitch,
-                                double* __restrict__ phase, long long ph_pitch, int t_begin, int t_count,
-                                const double2* __restrict__ tw, FftPlan plan, BluesteinTables bt) {
+// (cos, sin) of atan2(h, x) without the angle: (x, h) / hypot(x, h); atan2(0, 0) = 0 -> (1, 0).
+__device__ __forceinline__ double2 unit2(double x, double h) {
+    const double r2 = x * x + h * h;
+    if (r2 > 1e-280 && r2 < 1e280) {
+        const double inv = 1.0 / sqrt(r2);
+        return make_double2(x * inv, h * inv);
+    }
+    const double r = hypot(x, h);                       // zero, subnormal or huge: the slow, safe way
+    if (!(r > 0.0)) return make_double2(1.0, 0.0);
+    return make_double2(x / r, h / r);
+}
+
+// Hilbert transform of two real series per complex FFT: z = x1 + i x2; A(z) = ifft(h fft(z)) =
+// (x1 - H x2) + i (x2 + H x1)  =>  H x1 = Im A - x2,  H x2 = x1 - Re A.  `batch` such pairs per CTA pass through the
+// FFT side by side (more butterflies per barrier).
+//   CS == false: out = phase = atan2(H x, x)                          (hilbert_phase, _signal_tools.py:39-43)
+//   CS == true : out = (cos, sin) of that phase = (x, H x) / |(x, H x)| as double2 -- what the rank-2 eigenvector
+//                needs; no angle is ever formed on the fused path (no atan2 here, no sincos in k_eigvec_rank2).
+template <bool BLUESTEIN, bool CS>
+__global__ void k_hilbert(const double* __restrict__ x, long long n_series, int T, long long x_pitch,
+                          double* __restrict__ out, long long out_pitch, int t_begin, int t_count,
+                          const double2* __restrict__ tw, FftPlan plan, BluesteinTables bt, int batch) {
     extern __shared__ double2 sm[];
     const int bufn = BLUESTEIN ? bt.L : T;
+    const int stride = 2 * bufn;                       // per transform: two buffers
     const long long n_pairs = (n_series + 1) / 2;
+    const long long n_groups = (n_pairs + batch - 1) / batch;
     const int half = (T + 1) / 2;
     const double invT = 1.0 / (double)T;
-    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long pair0 = g * batch;
+        const int nb = (int)((n_pairs - pair0) < batch ? (n_pairs - pair0) : batch);
         double2* src = sm;
         double2* dst = sm + bufn;
-        const double* x1 = x + (2 * pair) * x_pitch;
-        const bool has2 = (2 * pair + 1) < n_series;
-        const double* x2 = x1 + (has2 ? x_pitch : 0);
-        for (int t = threadIdx.x; t < T; t += blockDim.x) src[t] = make_double2(x1[t], has2 ? x2[t] : 0.0);
-        __syncthreads();
-        if (BLUESTEIN) dft_bluestein(src, dst, T, tw, plan, bt);
-        else fft_forward(src, dst, tw, plan);
-        for (int k = threadIdx.x; k < T; k += blockDim.x) {
-            double h = (k == 0 || (2 * k == T)) ? 1.0 : (k < half ? 2.0 : 0.0);
-            double2 v = src[k];
-            src[k] = make_double2(h * v.x, -h * v.y);
+        for (int idx = threadIdx.x; idx < batch * T; idx += blockDim.x) {
+            const int bi = idx / T, t = idx - bi * T;
+            double2 v = make_double2(0.0, 0.0);
+            if (bi < nb) {
+                const long long s1 = 2 * (pair0 + bi);
+                const double* x1 = x + s1 * x_pitch;
+                v.x = x1[t];
+                if (s1 + 1 < n_series) v.y = x1[x_pitch + t];
+            }
+            src[(size_t)bi * stride + t] = v;
         }
         __syncthreads();
         if (BLUESTEIN) dft_bluestein(src, dst, T, tw, plan, bt);
-        else fft_forward(src, dst, tw, plan);
-        double* o1 = phase + (2 * pair) * ph_pitch;
-        double* o2 = o1 + ph_pitch;
-        for (int i = threadIdx.x; i < t_count; i += blockDim.x) {
+        else fft_forward(src, dst, tw, plan, batch, stride);
+        for (int idx = threadIdx.x; idx < batch * T; idx += blockDim.x) {
+            const int bi = idx / T, k = idx - bi * T;
+            const double h = (k == 0 || (2 * k == T)) ? 1.0 : (k < half ? 2.0 : 0.0);
+            double2* e = src + (size_t)bi * stride + k;
+            const double2 v = *e;
+            *e = make_double2(h * v.x, -h * v.y);
+        }
+        __syncthreads();
+        if (BLUESTEIN) dft_bluestein(src, dst, T, tw, plan, bt);
+        else fft_forward(src, dst, tw, plan, batch, stride);
+        for (int idx = threadIdx.x; idx < nb * t_count; idx += blockDim.x) {
+            const int bi = idx / t_count, i = idx - bi * t_count;
             const int t = t_begin + i;
-            const double2 r = src[t];
+            const long long s1 = 2 * (pair0 + bi);
+            const bool has2 = s1 + 1 < n_series;
+            const double* x1 = x + s1 * x_pitch;
+            const double2 r = src[(size_t)bi * stride + t];
             const double are = r.x * invT, aim = -r.y * invT;
-            const double v1 = x1[t], v2 = has2 ? x2[t] : 0.0;
-            o1[i] = atan2(aim - v2, v1);
-            if (has2) o2[i] = atan2(v1 - are, v2);
+            const double v1 = x1[t], v2 = has2 ? x1[x_pitch + t] : 0.0;
+            const double h1 = aim - v2, h2 = v1 - are;
+            if (CS) {
+                double2* o = reinterpret_cast<double2*>(out) + s1 * out_pitch + i;
+                o[0] = unit2(v1, h1);
+                if (has2) o[out_pitch] = unit2(v2, h2);
+            } else {
+                double* o = out + s1 * out_pitch + i;
+                o[0] = atan2(h1, v1);
+                if (has2) o[out_pitch] = atan2(h2, v2);
+            }
         }
         __syncthreads();
     }
@@ -287,7 +399,8 @@ __global__ void k_phase_coherence(const double* __restrict__ phase, int N, int T
 //   z_t = sum_j exp(2 i th_j);  phi = arg(z)/2;  v_j = cos(th_j - phi) / sqrt(N/2 + |z|/2)
 //   sign rule of _signal_tools.py:215-220.
 // ------------------------------------------------------------------------------------------------
-template <int TT>
+// CS == true: `phase` holds (cos, sin) pairs (double2; strides in double2 units) written by k_hilbert<.., true>.
+template <int TT, bool CS>
 __global__ void __launch_bounds__(256)
 k_eigvec_rank2(const double* __restrict__ phase, int N, int n_vol, long long subj_stride, long long row_pitch,
                double* __restrict__ lei, long long lei_pitch, float* __restrict__ xf, long long xf_pitch) {
@@ -301,14 +414,22 @@ k_eigvec_rank2(const double* __restrict__ phase, int N, int n_vol, long long sub
     const int tt = tid % TT;
     const int v0 = blockIdx.x * TT;
     const long long s = blockIdx.y;
-    const double* ph = phase + s * subj_stride;
+    const double* ph = phase + s * subj_stride * (CS ? 2 : 1);
     const bool live = (v0 + tt) < n_vol;
 
     double c2 = 0.0, s2 = 0.0;
     for (int e = tid; e < N * TT; e += 256) {
         const int j = e / TT;
         double sn = 0.0, cs = 0.0;
-        if (live) sincos(ph[(long long)j * row_pitch + v0 + tt], &sn, &cs);
+        if (live) {
+            if (CS) {
+                const double2 u = reinterpret_cast<const double2*>(ph)[(long long)j * row_pitch + v0 + tt];
+                cs = u.x;
+                sn = u.y;
+            } else {
+                sincos(ph[(long long)j * row_pitch + v0 + tt], &sn, &cs);
+            }
+        }
         sc[tt * NPAD + j] = cs;
         ss[tt * NPAD + j] = sn;
         c2 += cs * cs - sn * sn;
@@ -378,14 +499,29 @@ k_eigvec_rank2(const double* __restrict__ phase, int N, int n_vol, long long sub
     }
 }
 
-template <int TT>
+template <int TT, bool CS>
 static int launch_eigvec(const double* phase, int64_t S, int N, int n_vol, int64_t subj_stride, int64_t row_pitch,
                          double* lei, int64_t lei_pitch, float* xf, int64_t xf_pitch, cudaStream_t st) {
     const size_t smem = ((size_t)2 * TT * (N | 1) + 4 * 256 + 4 * TT) * sizeof(double);
-    LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_eigvec_rank2<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_eigvec_rank2<TT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n_vol + TT - 1) / TT, (unsigned)S);
-    k_eigvec_rank2<TT><<<grid, 256, smem, st>>>(phase, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch);
+    k_eigvec_rank2<TT, CS><<<grid, 256, smem, st>>>(phase, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch);
     return check_launch("k_eigvec_rank2");
+}
+
+// phase (CS == false) or (cos, sin) pairs (CS == true) -> eigenvector rows; picks the volume tile by shared memory.
+template <bool CS>
+static int eigvec_rank2(const double* phase, int64_t n_subjects, int N, int n_vol, int64_t subj_stride, int64_t row_pitch,
+                        double* lei, int64_t lei_pitch, float* xf, int64_t xf_pitch, cudaStream_t st) {
+    // largest tile of volumes whose cos/sin fit comfortably (two CTAs per SM when possible)
+    const size_t budget = 100 * 1024;
+    const size_t per_t = (size_t)2 * (N | 1) * sizeof(double);
+    if (16 * per_t + 9000 <= budget) return launch_eigvec<16, CS>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
+    if (8 * per_t + 9000 <= budget) return launch_eigvec<8, CS>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
+    if (4 * per_t + 9000 <= (size_t)max_smem_optin()) return launch_eigvec<4, CS>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
+    if (1 * per_t + 9000 <= (size_t)max_smem_optin()) return launch_eigvec<1, CS>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
+    set_error("N=%d too large for the rank-2 eigenvector kernel", N);
+    return LEIDA_ERR_UNSUPPORTED;
 }
 
 }  // namespace leida
@@ -403,15 +539,32 @@ extern "C" size_t leida_hilbert_workspace_bytes(int T) {
     return ((size_t)L * 2 + (size_t)T) * sizeof(double2);
 }
 
-extern "C" int leida_hilbert_phase_f64(const double* x, int64_t n_series, int T, int64_t x_pitch, double* phase,
-                                       int64_t phase_pitch, int t_begin, int t_count, void* workspace,
-                                       size_t workspace_bytes, leida_stream_t stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    LEIDA_REQUIRE(x && phase && workspace, "null pointer");
+// Threads per CTA for `batch` transforms per CTA: the count (multiple of 32, 64..256) that wastes the fewest thread
+// slots over the plan's passes (a pass has batch * n / radix butterflies).
+static int pick_threads(const FftPlan& plan, int batch) {
+    int best = 256;
+    double best_u = -1.0;
+    for (int th = 64; th <= 256; th += 32) {
+        double work = 0.0, slots = 0.0;
+        for (int f = 0; f < plan.nfac; ++f) {
+            const int tasks = batch * (plan.n / (plan.r1[f] * plan.r2[f]));
+            work += tasks;
+            slots += (double)((tasks + th - 1) / th) * th;
+        }
+        const double u = work / slots + 1e-4 * th;         // ties: more threads (more loads in flight)
+        if (u > best_u) { best_u = u; best = th; }
+    }
+    return best;
+}
+
+// cs == 0: out = phases (double, pitch in doubles); cs != 0: out = (cos, sin) pairs (double2, pitch in double2 units).
+static int hilbert_launch(const double* x, int64_t n_series, int T, int64_t x_pitch, double* out, int64_t out_pitch,
+                          int t_begin, int t_count, void* workspace, size_t workspace_bytes, int cs, cudaStream_t st) {
+    LEIDA_REQUIRE(x && out && workspace, "null pointer");
     LEIDA_REQUIRE(n_series >= 0 && T >= 1, "n_series >= 0 and T >= 1");
     LEIDA_REQUIRE(x_pitch >= T, "x_pitch >= T");
     LEIDA_REQUIRE(t_begin >= 0 && t_count >= 0 && t_begin + t_count <= T, "volume window inside [0,T)");
-    LEIDA_REQUIRE(phase_pitch >= t_count, "phase_pitch >= t_count");
+    LEIDA_REQUIRE(out_pitch >= t_count, "phase_pitch >= t_count");
     if (workspace_bytes < leida_hilbert_workspace_bytes(T)) {
         set_error("hilbert workspace too small: %zu < %zu", workspace_bytes, leida_hilbert_workspace_bytes(T));
         return LEIDA_ERR_WORKSPACE;
@@ -424,15 +577,26 @@ extern "C" int leida_hilbert_phase_f64(const double* x, int64_t n_series, int T,
     BluesteinTables bt{nullptr, nullptr, 0};
     double2* tw = (double2*)workspace;
     size_t smem;
-    int threads;
+    int threads, batch = 1;
     if (direct) {
-        smem = (size_t)2 * T * sizeof(double2);
-        if ((long long)smem > smem_max) {
+        const size_t per = (size_t)2 * T * sizeof(double2);
+        if ((long long)per > smem_max) {
             set_error("T=%d too long for the shared-memory FFT (max %d)", T, smem_max / 32);
             return LEIDA_ERR_UNSUPPORTED;
         }
+        // transforms per CTA: as many as keep two CTAs on an SM, at most 4, and no more than the work offers
+        while (batch < 4 && (batch + 1) * per + 1024 <= (size_t)smem_max / 2 && (long long)(batch + 1) * sm_count() * 2 <= n_pairs) ++batch;
+        if (const char* e = getenv("LEIDA_HILBERT_BATCH")) {          // tuning experiments only
+            const int b = atoi(e);
+            if (b >= 1 && (size_t)b * per <= (size_t)smem_max) batch = b;
+        }
+        smem = batch * per;
         k_twiddles<<<(T + 255) / 256, 256, 0, st>>>(tw, T);
-        threads = T >= 1024 ? 256 : (T >= 256 ? 128 : 64);
+        threads = pick_threads(plan, batch);
+        if (const char* e = getenv("LEIDA_HILBERT_THREADS")) {
+            const int t = atoi(e);
+            if (t >= 32 && t <= 256 && t % 32 == 0) threads = t;
+        }
     } else {
         const int L = next_pow2(2 * T - 1);
         smem = (size_t)2 * L * sizeof(double2);
@@ -459,18 +623,26 @@ extern "C" int leida_hilbert_phase_f64(const double* x, int64_t n_series, int T,
     int per_sm = (int)((size_t)smem_max / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    const long long n_groups = (n_pairs + batch - 1) / batch;
     long long grid = (long long)sm_count() * per_sm;
-    if (grid > n_pairs) grid = n_pairs;
-    if (direct) {
-        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_hilbert_phase<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hilbert_phase<false><<<(unsigned)grid, threads, smem, st>>>(x, n_series, T, x_pitch, phase, phase_pitch, t_begin,
-                                                                      t_count, tw, plan, bt);
-    } else {
-        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_hilbert_phase<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hilbert_phase<true><<<(unsigned)grid, threads, smem, st>>>(x, n_series, T, x_pitch, phase, phase_pitch, t_begin,
-                                                                     t_count, tw, plan, bt);
-    }
-    return check_launch("k_hilbert_phase");
+    if (grid > n_groups) grid = n_groups;
+#define LEIDA_HILBERT_LAUNCH(BL, CSV)                                                                                     \
+    do {                                                                                                                  \
+        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_hilbert<BL, CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_hilbert<BL, CSV><<<(unsigned)grid, threads, smem, st>>>(x, n_series, T, x_pitch, out, out_pitch, t_begin,     \
+                                                                  t_count, tw, plan, bt, batch);                         \
+    } while (0)
+    if (direct) { if (cs) LEIDA_HILBERT_LAUNCH(false, true); else LEIDA_HILBERT_LAUNCH(false, false); }
+    else { if (cs) LEIDA_HILBERT_LAUNCH(true, true); else LEIDA_HILBERT_LAUNCH(true, false); }
+#undef LEIDA_HILBERT_LAUNCH
+    return check_launch("k_hilbert");
+}
+
+extern "C" int leida_hilbert_phase_f64(const double* x, int64_t n_series, int T, int64_t x_pitch, double* phase,
+                                       int64_t phase_pitch, int t_begin, int t_count, void* workspace,
+                                       size_t workspace_bytes, leida_stream_t stream) {
+    return hilbert_launch(x, n_series, T, x_pitch, phase, phase_pitch, t_begin, t_count, workspace, workspace_bytes, 0,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int leida_phase_coherence_f64(const double* phase, int N, int T, int64_t phase_pitch, double* dfc,
@@ -496,24 +668,15 @@ extern "C" int leida_eigvec_rank2_f64(const double* phase, int64_t n_subjects, i
     LEIDA_REQUIRE(!lei || lei_pitch >= N, "lei_pitch >= N");
     LEIDA_REQUIRE(!xf || xf_pitch >= N, "xf_pitch >= N");
     if (n_subjects == 0 || n_vol == 0) return LEIDA_OK;
-    // largest tile of volumes whose cos/sin fit comfortably (two CTAs per SM when possible)
-    const size_t budget = 100 * 1024;
-    const size_t per_t = (size_t)2 * (N | 1) * sizeof(double);
-    if (16 * per_t + 9000 <= budget) return launch_eigvec<16>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
-    if (8 * per_t + 9000 <= budget) return launch_eigvec<8>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
-    if (4 * per_t + 9000 <= (size_t)max_smem_optin()) return launch_eigvec<4>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
-    if (1 * per_t + 9000 <= (size_t)max_smem_optin()) return launch_eigvec<1>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
-    set_error("N=%d too large for the rank-2 eigenvector kernel", N);
-    return LEIDA_ERR_UNSUPPORTED;
+    return eigvec_rank2<false>(phase, n_subjects, N, n_vol, subj_stride, row_pitch, lei, lei_pitch, xf, xf_pitch, st);
 }
 
-// Fused stage 1+2: phases of a chunk of subjects go to the workspace (trimmed to the T-2 used
-// volumes, pitch rounded up to 8 doubles so tiles are sector aligned) and are consumed while still
-// L2-resident.
+// Fused stage 1+2: the (cos, sin) pairs of a chunk of subjects go to the workspace (trimmed to the T-2 used volumes,
+// pitch rounded up to 8 so tiles are sector aligned) and are consumed by the eigenvector kernel while still L2-resident.
 static inline int64_t trimmed_pitch(int T) { return ((int64_t)(T - 2) + 7) / 8 * 8; }
 static inline int64_t fused_chunk_subjects(int64_t S, int N, int T) {
-    const int64_t per_subject = (int64_t)N * trimmed_pitch(T) * 8;
-    int64_t c = (48LL << 20) / (per_subject > 0 ? per_subject : 1);   // ~48 MB of phases per chunk (L2 = 126 MB)
+    const int64_t per_subject = (int64_t)N * trimmed_pitch(T) * 16;
+    int64_t c = (64LL << 20) / (per_subject > 0 ? per_subject : 1);   // ~64 MB of pairs per chunk (L2 = 126 MB)
     if (c < 1) c = 1;
     if (c > S) c = S;
     if (c > 65535) c = 65535;
@@ -524,7 +687,7 @@ extern "C" size_t leida_leading_eigvec_workspace_bytes(int64_t n_subjects, int N
     if (n_subjects < 1 || N < 1 || T < 3) return 0;
     const int64_t c = fused_chunk_subjects(n_subjects, N, T);
     size_t hil = (leida_hilbert_workspace_bytes(T) + 255) / 256 * 256;
-    return hil + (size_t)c * N * trimmed_pitch(T) * 8;
+    return hil + (size_t)c * N * trimmed_pitch(T) * 16;
 }
 
 extern "C" int leida_leading_eigvec_f64(const double* x, int64_t n_subjects, int N, int T, double* lei, int64_t lei_pitch,
@@ -532,6 +695,9 @@ extern "C" int leida_leading_eigvec_f64(const double* x, int64_t n_subjects, int
                                         leida_stream_t stream) {
     LEIDA_REQUIRE(x && workspace, "null pointer");
     LEIDA_REQUIRE(N >= 1 && T >= 3 && n_subjects >= 0, "N >= 1, T >= 3");
+    LEIDA_REQUIRE(lei || xf, "at least one output");
+    LEIDA_REQUIRE(!lei || lei_pitch >= N, "lei_pitch >= N");
+    LEIDA_REQUIRE(!xf || xf_pitch >= N, "xf_pitch >= N");
     if (workspace_bytes < leida_leading_eigvec_workspace_bytes(n_subjects, N, T)) {
         set_error("fused eigenvector workspace too small");
         return LEIDA_ERR_WORKSPACE;
@@ -539,16 +705,15 @@ extern "C" int leida_leading_eigvec_f64(const double* x, int64_t n_subjects, int
     if (n_subjects == 0) return LEIDA_OK;
     const int64_t chunk = fused_chunk_subjects(n_subjects, N, T);
     const size_t hil = (leida_hilbert_workspace_bytes(T) + 255) / 256 * 256;
-    double* ph = (double*)((char*)workspace + hil);
+    double* cs = (double*)((char*)workspace + hil);
     const int64_t tp = trimmed_pitch(T);
     const int n_vol = T - 2;
     for (int64_t s0 = 0; s0 < n_subjects; s0 += chunk) {
         const int64_t ns = (n_subjects - s0 < chunk) ? (n_subjects - s0) : chunk;
-        int rc = leida_hilbert_phase_f64(x + s0 * (int64_t)N * T, ns * N, T, T, ph, tp, 1, n_vol, workspace, hil, stream);
+        int rc = hilbert_launch(x + s0 * (int64_t)N * T, ns * N, T, T, cs, tp, 1, n_vol, workspace, hil, 1, (cudaStream_t)stream);
         if (rc) return rc;
-        rc = leida_eigvec_rank2_f64(ph, ns, N, n_vol, (int64_t)N * tp, tp,
-                                    lei ? lei + s0 * n_vol * lei_pitch : nullptr, lei_pitch,
-                                    xf ? xf + s0 * n_vol * xf_pitch : nullptr, xf_pitch, stream);
+        rc = eigvec_rank2<true>(cs, ns, N, n_vol, (int64_t)N * tp, tp, lei ? lei + s0 * n_vol * lei_pitch : nullptr, lei_pitch,
+                                xf ? xf + s0 * n_vol * xf_pitch : nullptr, xf_pitch, (cudaStream_t)stream);
         if (rc) return rc;
     }
     return LEIDA_OK;

@@ -17,6 +17,8 @@ for stage in "$@"; do
     ncu_list)  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-secondary > $OUT/ncu_list.log 2>&1; echo "ncu_list rc=$?" ;;
     mgpu)      for x in auto peer nccl; do LEIDA_EXCHANGE=$x timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py > $OUT/mgpu_check_${NG}gpu_$x.log 2>&1; echo "mgpu $x rc=$?"; grep "world=" $OUT/mgpu_check_${NG}gpu_$x.log; done ;;
     mbench)    for x in ${XCHG:-auto nccl}; do LEIDA_EXCHANGE=$x timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --steps 3 --warmup 2 > $OUT/bench_${NG}gpu_$x.json 2> $OUT/bench_${NG}gpu_$x.err; echo "mbench $x rc=$?"; done ;;
+    stage12)   timeout 600 python tools/stage12_probe.py > $OUT/stage12_probe.txt 2>&1; echo "stage12 rc=$?"; cat $OUT/stage12_probe.txt ;;
+    bench_dump) LEIDA_BENCH_DUMP=$OUT/per_launch.json timeout 900 python bench.py --steps 2 --warmup 2 --no-cpu --no-secondary > $OUT/bench_dump.json 2> $OUT/bench_dump.err; echo "bench_dump rc=$?" ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
