@@ -21,6 +21,10 @@ struct FftPlan {
     int nfac;
     unsigned char r1[20];
     unsigned char r2[20];
+    // internal twiddles of the composite passes: wint[slot(f)][m] = exp(-2 pi i m / (r1 r2)), m <= (r1-1)(r2-1) <= 9.
+    // Kernel parameters live in the constant bank and the index is a compile-time constant, so these cost nothing.
+    unsigned char slot[20];
+    double2 wint[6][10];
 };
 
 static bool make_plan(int n, FftPlan& p) {
@@ -53,6 +57,25 @@ static bool make_plan(int n, FftPlan& p) {
         ++p.nfac;
     }
     for (int i = 0; i < nbig; ++i) { p.r1[p.nfac] = (unsigned char)big[i]; p.r2[p.nfac] = 1; ++p.nfac; }
+    // at most 6 distinct composite radices exist (16, 15, 12, 10, 9, 8, 6 minus what n admits); passes share slots
+    int n_slots = 0, slot_r[6];
+    for (int f = 0; f < p.nfac; ++f) {
+        p.slot[f] = 0;
+        if (p.r2[f] == 1) continue;
+        const int R = p.r1[f] * p.r2[f];
+        int sl = -1;
+        for (int i = 0; i < n_slots; ++i) if (slot_r[i] == R) sl = i;
+        if (sl < 0) {
+            if (n_slots == 6) { p.r2[f] = 1; /* cannot happen: split back into a plain pass */ return false; }
+            sl = n_slots++;
+            slot_r[sl] = R;
+            for (int m2 = 0; m2 < 10; ++m2) {
+                const double a = -2.0 * 3.14159265358979323846 * (double)m2 / (double)R;
+                p.wint[sl][m2] = make_double2(cos(a), sin(a));
+            }
+        }
+        p.slot[f] = (unsigned char)sl;
+    }
     return true;
 }
 
@@ -114,9 +137,9 @@ __device__ __forceinline__ void butterfly<5>(double2* v) {
 }
 
 // r1*r2-point DFT in registers, natural order in and out: X[b + R1 c] = sum_a w_R2^{ac} w_R^{ab} sum_d w_R1^{db} x[a + R2 d].
-// w_R^m = tw[m * wstep] (wstep = n / R; R divides n).
+// w_R^m = wint[m] (FftPlan::wint, constant bank).
 template <int R1, int R2>
-__device__ __forceinline__ void butterfly2(double2* v, const double2* __restrict__ tw, int wstep) {
+__device__ __forceinline__ void butterfly2(double2* v, const double2* __restrict__ wint) {
     constexpr int R = R1 * R2;
     double2 y[R];
 #pragma unroll
@@ -126,7 +149,7 @@ __device__ __forceinline__ void butterfly2(double2* v, const double2* __restrict
         for (int d = 0; d < R1; ++d) t[d] = v[a + R2 * d];
         butterfly<R1>(t);
 #pragma unroll
-        for (int b = 0; b < R1; ++b) y[a * R1 + b] = (a * b) ? cmul(t[b], __ldg(&tw[(a * b) * wstep])) : t[b];
+        for (int b = 0; b < R1; ++b) y[a * R1 + b] = (a * b) ? cmul(t[b], wint[a * b]) : t[b];
     }
 #pragma unroll
     for (int b = 0; b < R1; ++b) {
@@ -141,28 +164,47 @@ __device__ __forceinline__ void butterfly2(double2* v, const double2* __restrict
 
 // One Stockham pass of radix R1*R2 over `batch` transforms held side by side in shared memory (transform i at
 // in + i * stride): batch * n/R butterflies spread over the CTA.
+// w^j for j = 1..R-1 from w = w^1 with multiplication depth <= 4 (w^2, w^4, w^8 by squaring, the rest as products of
+// those): one table load per butterfly instead of R-1 scattered 16-byte gathers, at ~4 ulp.
+template <int R>
+__device__ __forceinline__ void twiddle_powers(double2 w, double2* pw) {
+    pw[1] = w;
+#pragma unroll
+    for (int j = 2; j < R; ++j) {
+        const int hb = j >= 8 ? 8 : j >= 4 ? 4 : 2;       // highest power of two <= j
+        pw[j] = (j == hb) ? cmul(pw[j / 2], pw[j / 2]) : cmul(pw[hb], pw[j - hb]);
+    }
+}
+
 template <int R1, int R2>
 __device__ __forceinline__ void fft_pass(const double2* __restrict__ in, double2* __restrict__ out,
-                                         const double2* __restrict__ tw, int n, int len, int s, int batch, int stride) {
+                                         const double2* __restrict__ tw, const double2* __restrict__ wint, int n, int len,
+                                         int s, int batch, int stride) {
     constexpr int R = R1 * R2;
     const int m = len / R, nb = n / R, tstep = n / len;
+    // idx / nb and i / s by float reciprocals (exact for operands < 2^20; the sizes here are < 2^14)
+    const float inv_nb = 1.0f / (float)nb, inv_s = 1.0f / (float)s;
     for (int idx = threadIdx.x; idx < nb * batch; idx += blockDim.x) {
-        const int bi = idx / nb, i = idx - bi * nb;
-        const int p = i / s, q = i - p * s;
+        const int bi = batch == 1 ? 0 : (int)(((float)idx + 0.5f) * inv_nb);
+        const int i = idx - bi * nb;
+        const int p = s == 1 ? i : (m == 1 ? 0 : (int)(((float)i + 0.5f) * inv_s));
+        const int q = i - p * s;
         const double2* ib = in + (size_t)bi * stride;
         double2 v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = ib[q + s * (p + k * m)];
         if constexpr (R2 == 1) butterfly<R1>(v);
-        else butterfly2<R1, R2>(v, tw, n / R);
+        else butterfly2<R1, R2>(v, wint);
         double2* o = out + (size_t)bi * stride + q + s * (R * p);
         o[0] = v[0];
         if (p == 0) {
 #pragma unroll
             for (int j = 1; j < R; ++j) o[s * j] = v[j];
         } else {
+            double2 pw[R];
+            twiddle_powers<R>(__ldg(&tw[p * tstep]), pw);
 #pragma unroll
-            for (int j = 1; j < R; ++j) o[s * j] = cmul(v[j], __ldg(&tw[p * j * tstep]));
+            for (int j = 1; j < R; ++j) o[s * j] = cmul(v[j], pw[j]);
         }
     }
 }
@@ -195,17 +237,17 @@ __device__ __forceinline__ void fft_forward(double2*& src, double2*& dst, const 
     for (int f = 0; f < plan.nfac; ++f) {
         const int r1 = plan.r1[f], r2 = plan.r2[f];
         switch (r1 * 8 + r2) {
-            case 4 * 8 + 4: fft_pass<4, 4>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 5 * 8 + 3: fft_pass<5, 3>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 5 * 8 + 2: fft_pass<5, 2>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 4 * 8 + 3: fft_pass<4, 3>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 4 * 8 + 2: fft_pass<4, 2>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 3 * 8 + 3: fft_pass<3, 3>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 3 * 8 + 2: fft_pass<3, 2>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 5 * 8 + 1: fft_pass<5, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 4 * 8 + 1: fft_pass<4, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 3 * 8 + 1: fft_pass<3, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
-            case 2 * 8 + 1: fft_pass<2, 1>(src, dst, tw, plan.n, len, s, batch, stride); break;
+            case 4 * 8 + 4: fft_pass<4, 4>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 5 * 8 + 3: fft_pass<5, 3>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 5 * 8 + 2: fft_pass<5, 2>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 4 * 8 + 3: fft_pass<4, 3>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 4 * 8 + 2: fft_pass<4, 2>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 3 * 8 + 3: fft_pass<3, 3>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 3 * 8 + 2: fft_pass<3, 2>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 5 * 8 + 1: fft_pass<5, 1>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 4 * 8 + 1: fft_pass<4, 1>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 3 * 8 + 1: fft_pass<3, 1>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
+            case 2 * 8 + 1: fft_pass<2, 1>(src, dst, tw, plan.wint[plan.slot[f]], plan.n, len, s, batch, stride); break;
             default: fft_pass_generic(src, dst, tw, plan.n, len, s, r1, batch, stride); break;
         }
         __syncthreads();
@@ -290,7 +332,7 @@ __global__ void k_bluestein_bhat(const double2* __restrict__ chirp, const double
 __device__ __forceinline__ double2 unit2(double x, double h) {
     const double r2 = x * x + h * h;
     if (r2 > 1e-280 && r2 < 1e280) {
-        const double inv = 1.0 / sqrt(r2);
+        const double inv = rsqrt(r2);                   // <= 1 ulp (CUDA math API): cheaper than sqrt + divide
         return make_double2(x * inv, h * inv);
     }
     const double r = hypot(x, h);                       // zero, subnormal or huge: the slow, safe way
@@ -305,7 +347,8 @@ __device__ __forceinline__ double2 unit2(double x, double h) {
 //   CS == true : out = (cos, sin) of that phase = (x, H x) / |(x, H x)| as double2 -- what the rank-2 eigenvector
 //                needs; no angle is ever formed on the fused path (no atan2 here, no sincos in k_eigvec_rank2).
 template <bool BLUESTEIN, bool CS>
-__global__ void k_hilbert(const double* __restrict__ x, long long n_series, int T, long long x_pitch,
+__global__ void __launch_bounds__(256, 2)
+k_hilbert(const double* __restrict__ x, long long n_series, int T, long long x_pitch,
                           double* __restrict__ out, long long out_pitch, int t_begin, int t_count,
                           const double2* __restrict__ tw, FftPlan plan, BluesteinTables bt, int batch) {
     extern __shared__ double2 sm[];
@@ -321,7 +364,7 @@ __global__ void k_hilbert(const double* __restrict__ x, long long n_series, int 
         double2* src = sm;
         double2* dst = sm + bufn;
         for (int idx = threadIdx.x; idx < batch * T; idx += blockDim.x) {
-            const int bi = idx / T, t = idx - bi * T;
+            const int bi = batch == 1 ? 0 : idx / T, t = idx - bi * T;
             double2 v = make_double2(0.0, 0.0);
             if (bi < nb) {
                 const long long s1 = 2 * (pair0 + bi);
@@ -335,7 +378,7 @@ __global__ void k_hilbert(const double* __restrict__ x, long long n_series, int 
         if (BLUESTEIN) dft_bluestein(src, dst, T, tw, plan, bt);
         else fft_forward(src, dst, tw, plan, batch, stride);
         for (int idx = threadIdx.x; idx < batch * T; idx += blockDim.x) {
-            const int bi = idx / T, k = idx - bi * T;
+            const int bi = batch == 1 ? 0 : idx / T, k = idx - bi * T;
             const double h = (k == 0 || (2 * k == T)) ? 1.0 : (k < half ? 2.0 : 0.0);
             double2* e = src + (size_t)bi * stride + k;
             const double2 v = *e;
@@ -345,7 +388,7 @@ __global__ void k_hilbert(const double* __restrict__ x, long long n_series, int 
         if (BLUESTEIN) dft_bluestein(src, dst, T, tw, plan, bt);
         else fft_forward(src, dst, tw, plan, batch, stride);
         for (int idx = threadIdx.x; idx < nb * t_count; idx += blockDim.x) {
-            const int bi = idx / t_count, i = idx - bi * t_count;
+            const int bi = batch == 1 ? 0 : idx / t_count, i = idx - bi * t_count;
             const int t = t_begin + i;
             const long long s1 = 2 * (pair0 + bi);
             const bool has2 = s1 + 1 < n_series;
@@ -584,8 +627,10 @@ static int hilbert_launch(const double* x, int64_t n_series, int T, int64_t x_pi
             set_error("T=%d too long for the shared-memory FFT (max %d)", T, smem_max / 32);
             return LEIDA_ERR_UNSUPPORTED;
         }
-        // transforms per CTA: as many as keep two CTAs on an SM, at most 4, and no more than the work offers
-        while (batch < 4 && (batch + 1) * per + 1024 <= (size_t)smem_max / 2 && (long long)(batch + 1) * sm_count() * 2 <= n_pairs) ++batch;
+        // One transform pair per CTA and several small CTAs per SM (measured, profiles/r02_stage12.md): the kernel is
+        // bound by latency (input loads, barriers between passes), which other resident CTAs hide better than a wider
+        // CTA does; short transforms are batched so that a CTA still has a warp's worth of butterflies per pass.
+        while (batch < 8 && (batch + 1) * per <= (size_t)16 << 10 && (long long)(batch + 1) * sm_count() * 4 <= n_pairs) ++batch;
         if (const char* e = getenv("LEIDA_HILBERT_BATCH")) {          // tuning experiments only
             const int b = atoi(e);
             if (b >= 1 && (size_t)b * per <= (size_t)smem_max) batch = b;
@@ -593,6 +638,7 @@ static int hilbert_launch(const double* x, int64_t n_series, int T, int64_t x_pi
         smem = batch * per;
         k_twiddles<<<(T + 255) / 256, 256, 0, st>>>(tw, T);
         threads = pick_threads(plan, batch);
+        if (batch == 1 && T >= 1024 && threads < 128) threads = 128;
         if (const char* e = getenv("LEIDA_HILBERT_THREADS")) {
             const int t = atoi(e);
             if (t >= 32 && t <= 256 && t % 32 == 0) threads = t;

@@ -19,6 +19,7 @@ for stage in "$@"; do
     mbench)    for x in ${XCHG:-auto nccl}; do LEIDA_EXCHANGE=$x timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --steps 3 --warmup 2 > $OUT/bench_${NG}gpu_$x.json 2> $OUT/bench_${NG}gpu_$x.err; echo "mbench $x rc=$?"; done ;;
     stage12)   timeout 600 python tools/stage12_probe.py > $OUT/stage12_probe.txt 2>&1; echo "stage12 rc=$?"; cat $OUT/stage12_probe.txt ;;
     bench_dump) LEIDA_BENCH_DUMP=$OUT/per_launch.json timeout 900 python bench.py --steps 2 --warmup 2 --no-cpu --no-secondary > $OUT/bench_dump.json 2> $OUT/bench_dump.err; echo "bench_dump rc=$?" ;;
+    ncu_stage12) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_hilbert|k_eigvec_rank2" -c 4 -o $OUT/stage12 -f python tools/stage12_probe.py 60 > $OUT/ncu_stage12.log 2>&1; echo "ncu_stage12 rc=$?" ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
