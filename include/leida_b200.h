@@ -40,12 +40,30 @@ int         leida_device_sm_count(void);
 int64_t     leida_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Stage 0 (optional) -- clean_signals   (signal_tools/_signal_tools.py:66-133 -> nilearn.signal.clean, nilearn 0.9.1:
+ * linear detrend, Butterworth band-pass applied forward and backward (scipy.signal.filtfilt), standardisation)
+ * x: n_series rows of length T (row i at x + i*x_pitch) -> out, same layout (out == x is allowed).
+ * detrend != 0: subtract the mean and the least-squares line.  standardize: 0 none, 1 z-score, 2 percent signal change.
+ * b, a, zi: HOST arrays -- the n_coef transfer-function coefficients of scipy.signal.butter(5, Wn, btype, output='ba')
+ * and the n_coef-1 steady-state initial conditions scipy.signal.lfilter_zi(b, a); the filter design is scalar host work
+ * done by the caller.  n_coef = 0: no filtering; otherwise 2 <= n_coef <= 12 and T > 3*n_coef (filtfilt's odd padding).
+ * One thread per series runs scipy's direct-form-II-transposed recursion over the odd-extended series in both
+ * directions; data is held time-major in the workspace so that every access is coalesced.
+ * ------------------------------------------------------------------------------------------ */
+size_t leida_clean_workspace_bytes(int64_t n_series, int T, int n_coef);
+int    leida_clean_signals_f64(const double* x, int64_t n_series, int T, int64_t x_pitch,
+                               double* out, int64_t out_pitch, int detrend, int standardize,
+                               const double* b, const double* a, const double* zi, int n_coef,
+                               void* workspace, size_t workspace_bytes, leida_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage 1 -- hilbert_phase          (signal_tools/_signal_tools.py:24-44)
  * n_series real series of length T (row i at x + i*x_pitch) -> instantaneous phase in (-pi, pi].
  * Only volumes [t_begin, t_begin+t_count) are written, to phase + i*phase_pitch + (t - t_begin);
  * t_begin=0,t_count=T gives the reference's full (N,T) output.
- * Shared-memory mixed-radix FFT (radices 2,3,4,5 and generic primes <= 31); other lengths use
- * Bluestein.  Supported: T <= 7168 when T factors into primes <= 31, else T <= 2048.
+ * Shared-memory Stockham FFT in fp64, two real series per complex transform; composite radices up to 16 are done in
+ * registers (T = 1200 = 15 x 5 x 16: three passes), generic primes <= 31; other lengths use Bluestein.
+ * Supported: T <= 7168 when T factors into primes <= 31, else T <= 2048.
  * ------------------------------------------------------------------------------------------ */
 size_t leida_hilbert_workspace_bytes(int T);
 int    leida_hilbert_phase_f64(const double* x, int64_t n_series, int T, int64_t x_pitch,
@@ -75,7 +93,8 @@ int leida_eigvec_rank2_f64(const double* phase, int64_t n_subjects, int N, int n
                            leida_stream_t stream);
 
 /* Fused stage 1+2 for the Leida pipeline (_leida.py:287-289): x (S, N, T) contiguous fp64 ->
- * eigenvector rows.  Phases of a chunk of subjects are kept in `workspace` (L2-sized chunks). */
+ * eigenvector rows.  No angle is formed on this path: the Hilbert kernel writes (cos, sin) = (x, Hx)/|(x, Hx)| of a
+ * chunk of subjects to `workspace` (L2-sized chunks) and the rank-2 kernel consumes them (no atan2, no sincos). */
 size_t leida_leading_eigvec_workspace_bytes(int64_t n_subjects, int N, int T);
 int    leida_leading_eigvec_f64(const double* x, int64_t n_subjects, int N, int T,
                                 double* lei, int64_t lei_pitch, float* xf, int64_t xf_pitch,

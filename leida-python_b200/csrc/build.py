@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "pyleida", "_lib")
 OUT = os.path.join(OUT_DIR, "libleida_b200.so")
-SOURCES = ["capi.cu", "signal.cu", "eigdense.cu", "kmeans.cu", "kmeans_tc.cu", "scores.cu", "dynamics.cu", "stats.cu"]
+SOURCES = ["capi.cu", "signal.cu", "clean.cu", "eigdense.cu", "kmeans.cu", "kmeans_tc.cu", "scores.cu", "dynamics.cu", "stats.cu"]
 HEADERS = [os.path.join(HERE, "common.cuh"), os.path.join(ROOT, "include", "leida_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -788,50 +788,58 @@ k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long
 }
 
 // Distortion, second form (rows up to 512 columns): the L2 traffic of the kernel above is one centroid row per (row, run)
-// pair -- 546 GB at 1.2 M rows x 285 runs x 400 columns, which is what bounds it.  Here a CTA owns a tile of 48 rows
-// held in REGISTERS as doubles (12 warps x 4 rows, lanes stride the columns) and walks over all runs; each run's K
-// centroid rows are staged once per tile in shared memory (cp.async, double buffered) and every (row, run) dot product
-// reads its centroid from there: L2 traffic / 4-5, and when the four rows of a warp carry the same label (consecutive
-// volumes of a subject usually do -- that persistence is what dwell times measure) one shared-memory read and one
-// float->double conversion serve all four.  Per-row arithmetic (lane-strided fp64 FMA chain, fixed butterfly) does not
-// depend on the neighbours, so results are independent of tiling and sharding.  Persistent CTAs keep the per-run sums in
-// shared memory and issue their global atomics once.
+// pair -- 546 GB at 1.2 M rows x 285 runs x 400 columns, which is what bounds it.  Here a CTA owns a tile of rows held
+// in REGISTERS as doubles (12 warps x Q quads of 4 rows, lanes stride the columns) and walks over all runs; each run's
+// K centroid rows are staged once per tile in shared memory (cp.async ring, NST runs deep, one barrier per run) and
+// every (row, run) dot product reads its centroid from there: L2 traffic / 4-5, and when the four rows of a quad carry
+// the same label (consecutive volumes of a subject usually do -- that persistence is what dwell times measure) one
+// shared-memory read and one float->double conversion serve all four.  Per-row arithmetic (lane-strided fp64 FMA
+// chain, fixed butterfly) does not depend on the neighbours, so results are independent of tiling and sharding.
+// Persistent CTAs keep the per-run sums in shared memory and issue their global atomics once.
 constexpr int D2_WARPS = 12;
 constexpr int D2_THREADS = 32 * D2_WARPS;
-constexpr int D2_RPW = 4;
-constexpr int D2_ROWS = D2_WARPS * D2_RPW;
 
-template <int CPL>
+template <int CPL, int Q, int NST>
 __global__ void __launch_bounds__(D2_THREADS, 1)
 k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm, long long M, int XP, int n_runs,
                    const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0,
                    const float* __restrict__ cent, const double* __restrict__ cnorm, const int32_t* __restrict__ labels,
                    long long* state, int kmax) {
+    constexpr int RPW = 4 * Q;                       // rows per warp
+    constexpr int ROWS = D2_WARPS * RPW;             // rows per tile
     extern __shared__ __align__(16) unsigned char d2raw[];
-    float* cbuf = reinterpret_cast<float*>(d2raw);                                   // [2][kmax * XP]
-    double* cnb = reinterpret_cast<double*>(cbuf + (size_t)2 * kmax * XP);           // [2][kmax]
-    unsigned long long* s_hi = reinterpret_cast<unsigned long long*>(cnb + 2 * kmax);   // [n_runs]
+    float* cbuf = reinterpret_cast<float*>(d2raw);                                   // [NST][kmax * XP]
+    double* cnb = reinterpret_cast<double*>(cbuf + (size_t)NST * kmax * XP);         // [NST][kmax]
+    unsigned long long* s_hi = reinterpret_cast<unsigned long long*>(cnb + NST * kmax);   // [n_runs]
     unsigned long long* s_lo = s_hi + n_runs;
+    int* s_k = reinterpret_cast<int*>(s_lo + n_runs);                                // [n_runs]
+    int* s_c0 = s_k + n_runs;                                                        // [n_runs]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < n_runs; i += D2_THREADS) { s_hi[i] = 0; s_lo[i] = 0; }
-    const long long n_tiles = (M + D2_ROWS - 1) / D2_ROWS;
+    for (int i = threadIdx.x; i < n_runs; i += D2_THREADS) {
+        s_hi[i] = 0; s_lo[i] = 0; s_k[i] = run_k[i]; s_c0[i] = run_crow0[i];
+    }
+    __syncthreads();
+    const long long n_tiles = (M + ROWS - 1) / ROWS;
 
-    auto stage = [&](int run, int b) {
-        const int K = run_k[run], crow0 = run_crow0[run];
-        const float* src = cent + (long long)crow0 * XP;
-        float* dst = cbuf + (size_t)b * kmax * XP;
-        const int chunks = K * (XP / 4);
-        for (int i = threadIdx.x; i < chunks; i += D2_THREADS) cp_async16(dst + 4 * i, src + 4 * (long long)i, true);
-        if (threadIdx.x < K) cnb[b * kmax + threadIdx.x] = cnorm[crow0 + threadIdx.x];
+    auto stage = [&](int run) {                      // one cp.async group per call, also when there is nothing to copy
+        if (run < n_runs) {
+            const int b = run % NST;
+            const int K = s_k[run], crow0 = s_c0[run];
+            const float* src = cent + (long long)crow0 * XP;
+            float* dst = cbuf + (size_t)b * kmax * XP;
+            const int chunks = K * (XP / 4);
+            for (int i = threadIdx.x; i < chunks; i += D2_THREADS) cp_async16(dst + 4 * i, src + 4 * (long long)i, true);
+            if (threadIdx.x < K) cnb[b * kmax + threadIdx.x] = cnorm[crow0 + threadIdx.x];
+        }
         cp_async_commit();
     };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row0 = tile * D2_ROWS + (long long)w * D2_RPW;
-        double xv[D2_RPW][CPL];
-        double xn[D2_RPW];
+        const long long row0 = tile * ROWS + (long long)w * RPW;
+        double xv[RPW][CPL];
+        double xn[RPW];
 #pragma unroll
-        for (int u = 0; u < D2_RPW; ++u) {
+        for (int u = 0; u < RPW; ++u) {
             const long long row = row0 + u;
             const bool ok = row < M;
             const float* xr = X + (ok ? row : 0) * XP;
@@ -842,74 +850,77 @@ k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm
                 xv[u][i] = (ok && j < XP) ? (double)xr[j] : 0.0;
             }
         }
-        // labels of the warp's rows for the current run live in lanes 0..3; the next run's are prefetched
-        const bool lab_lane = lane < D2_RPW && row0 + lane < M;
-        int lab_cur = lab_lane ? labels[row0 + lane] : 0;
-        __syncthreads();                       // previous tile's last compute is done: buffer 0 may be refilled
-        stage(0, 0);
+        // labels of the warp's rows: lane u < RPW holds row u's label of the current run; two runs are prefetched
+        const bool lab_lane = lane < RPW && row0 + lane < M;
+        const int32_t* lab_ptr = labels + row0 + lane;
+        int lab_cur = lab_lane ? lab_ptr[0] : 0;
+        int lab_n1 = (lab_lane && 1 < n_runs) ? lab_ptr[(long long)M] : 0;
+        int lab_n2 = (lab_lane && 2 < n_runs) ? lab_ptr[2 * (long long)M] : 0;
+        __syncthreads();                       // the previous tile's last compute is done: the ring may be refilled
+#pragma unroll
+        for (int r = 0; r < NST - 1; ++r) stage(r);
         for (int r = 0; r < n_runs; ++r) {
-            const int b = r & 1;
-            int lab_next = 0;
-            if (r + 1 < n_runs) {
-                if (lab_lane) lab_next = labels[(long long)(r + 1) * M + row0 + lane];
-                stage(r + 1, b ^ 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncthreads();                   // run r's centroids have landed for every thread
-            int l[D2_RPW];
-#pragma unroll
-            for (int u = 0; u < D2_RPW; ++u) {
-                l[u] = __shfl_sync(0xffffffffu, lab_cur, u);
-                if (l[u] < 0) l[u] = 0;
-            }
+            const int b = r % NST;
+            cp_async_wait<NST - 2>();          // this thread's copies of run r have landed
+            __syncthreads();                   // ... everyone's have, and everyone finished computing run r - 1
+            stage(r + NST - 1);                // refills the buffer run r - 1 used
+            const int lab_n3 = (lab_lane && r + 3 < n_runs) ? lab_ptr[(long long)(r + 3) * M] : 0;
             const float* cb = cbuf + (size_t)b * kmax * XP;
-            double s[D2_RPW];
+            unsigned long long hi = 0, lo = 0;
 #pragma unroll
-            for (int u = 0; u < D2_RPW; ++u) s[u] = 0.0;
-            if (l[0] == l[1] && l[1] == l[2] && l[2] == l[3]) {
-                const float* c0 = cb + (size_t)l[0] * XP;
+            for (int qd = 0; qd < Q; ++qd) {
+                int l[4];
 #pragma unroll
-                for (int i = 0; i < CPL; ++i) {
-                    const int j = lane + 32 * i;
-                    const double cv = j < XP ? (double)c0[j] : 0.0;
-#pragma unroll
-                    for (int u = 0; u < D2_RPW; ++u) s[u] = fma(xv[u][i], cv, s[u]);
+                for (int u = 0; u < 4; ++u) {
+                    l[u] = __shfl_sync(0xffffffffu, lab_cur, 4 * qd + u);
+                    if (l[u] < 0) l[u] = 0;
                 }
-            } else {
+                double s[4] = {0.0, 0.0, 0.0, 0.0};
+                if (l[0] == l[1] && l[1] == l[2] && l[2] == l[3]) {
+                    const float* c0 = cb + (size_t)l[0] * XP;
 #pragma unroll
-                for (int i = 0; i < CPL; ++i) {
-                    const int j = lane + 32 * i;
+                    for (int i = 0; i < CPL; ++i) {
+                        const int j = lane + 32 * i;
+                        const double cv = j < XP ? (double)c0[j] : 0.0;
 #pragma unroll
-                    for (int u = 0; u < D2_RPW; ++u) {
-                        const double cv = j < XP ? (double)cb[(size_t)l[u] * XP + j] : 0.0;
-                        s[u] = fma(xv[u][i], cv, s[u]);
+                        for (int u = 0; u < 4; ++u) s[u] = fma(xv[4 * qd + u][i], cv, s[u]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) {
+                        const int j = lane + 32 * i;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double cv = j < XP ? (double)cb[(size_t)l[u] * XP + j] : 0.0;
+                            s[u] = fma(xv[4 * qd + u][i], cv, s[u]);
+                        }
                     }
                 }
-            }
-            // four sums over 32 lanes with 6 shuffles: halve the values held per lane twice, then a plain butterfly
-            const bool b4 = lane & 16, b3 = lane & 8;
-            double a0 = b4 ? s[2] : s[0], a1 = b4 ? s[3] : s[1];
-            a0 += __shfl_xor_sync(0xffffffffu, b4 ? s[0] : s[2], 16);
-            a1 += __shfl_xor_sync(0xffffffffu, b4 ? s[1] : s[3], 16);
-            double t = b3 ? a1 : a0;
-            t += __shfl_xor_sync(0xffffffffu, b3 ? a0 : a1, 8);
-            t += __shfl_xor_sync(0xffffffffu, t, 4);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            // lanes 0, 8, 16, 24 finish rows 0, 1, 2, 3
-            const int u_mine = (b4 ? 2 : 0) + (b3 ? 1 : 0);
-            unsigned long long hi = 0, lo = 0;
-            if ((lane & 7) == 0 && row0 + u_mine < M) {
-                const double d = cosine_distance(t, xn[u_mine], cnb[b * kmax + l[u_mine]]);
-                const double d2 = d * d * kFracScale;   // exact scaling
-                if (d2 == d2) {
-                    const double f = floor(d2);
-                    hi = (unsigned long long)(long long)f;
-                    lo = (unsigned long long)(long long)floor((d2 - f) * kFracScale);
-                } else {
-                    hi = 0x4000000000000000ULL;         // poison: NaN distance
+                // four sums over 32 lanes with 6 shuffles: halve the values held per lane twice, then a plain butterfly
+                const bool b4 = lane & 16, b3 = lane & 8;
+                double a0 = b4 ? s[2] : s[0], a1 = b4 ? s[3] : s[1];
+                a0 += __shfl_xor_sync(0xffffffffu, b4 ? s[0] : s[2], 16);
+                a1 += __shfl_xor_sync(0xffffffffu, b4 ? s[1] : s[3], 16);
+                double t = b3 ? a1 : a0;
+                t += __shfl_xor_sync(0xffffffffu, b3 ? a0 : a1, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                // lanes 0, 8, 16, 24 finish rows 0, 1, 2, 3 of the quad
+                const int u_mine = (b4 ? 2 : 0) + (b3 ? 1 : 0);
+                double xn_mine = xn[4 * qd];
+#pragma unroll
+                for (int u = 1; u < 4; ++u) if (u_mine == u) xn_mine = xn[4 * qd + u];
+                if ((lane & 7) == 0 && row0 + 4 * qd + u_mine < M) {
+                    const double d = cosine_distance(t, xn_mine, cnb[b * kmax + l[u_mine]]);
+                    const double d2 = d * d * kFracScale;   // exact scaling
+                    if (d2 == d2) {
+                        const double f = floor(d2);
+                        hi += (unsigned long long)(long long)f;
+                        lo += (unsigned long long)(long long)floor((d2 - f) * kFracScale);
+                    } else {
+                        hi += 0x4000000000000000ULL;        // poison: NaN distance
+                    }
                 }
             }
             hi += __shfl_xor_sync(0xffffffffu, hi, 8);
@@ -920,9 +931,9 @@ k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm
                 atomicAdd(&s_hi[r], hi);
                 atomicAdd(&s_lo[r], lo);
             }
-            lab_cur = lab_next;
-            __syncthreads();                   // everyone is done with buffer b: it is refilled two runs from now
+            lab_cur = lab_n1; lab_n1 = lab_n2; lab_n2 = lab_n3;
         }
+        cp_async_wait<0>();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_runs; i += D2_THREADS) {
@@ -1230,22 +1241,31 @@ extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int6
             LEIDA_CUDA_TRY(cudaStreamSynchronize(st));
             for (int i = 0; i < n_runs; ++i) kmax = hk[i] > kmax ? hk[i] : kmax;
         }
-        const size_t smem2 = (size_t)2 * kmax * x_pitch * sizeof(float) + (size_t)2 * kmax * sizeof(double) +
-                             (size_t)2 * n_runs * sizeof(unsigned long long) + 64;
+        // ring depth: as deep as shared memory allows, 2..4 runs
+        const size_t per_stage = (size_t)kmax * x_pitch * sizeof(float) + (size_t)kmax * sizeof(double);
+        const size_t fixed2 = (size_t)n_runs * (2 * sizeof(unsigned long long) + 2 * sizeof(int)) + 64;
+        int nst = 4;
+        while (nst > 2 && nst * per_stage + fixed2 > (size_t)max_smem_optin()) --nst;
+        const size_t smem2 = nst * per_stage + fixed2;
         const bool tiled = x_pitch <= 512 && smem2 <= (size_t)max_smem_optin() && getenv("LEIDA_DISTORTION_LEGACY") == nullptr;
         if (tiled) {
-            const long long n_tiles = (M + D2_ROWS - 1) / D2_ROWS;
-            const unsigned g2 = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());
-#define LEIDA_D2(CPLV)                                                                                                   \
-    do {                                                                                                                 \
-        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_distortion_tiled<CPLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-        k_distortion_tiled<CPLV><<<g2, D2_THREADS, smem2, st>>>(X, xnorm, M, (int)x_pitch, n_runs, run_k, run_crow0, cent, \
-                                                                cnorm, labels, (long long*)state, kmax);                \
+#define LEIDA_D2(CPLV, QV, NSTV)                                                                                          \
+    do {                                                                                                                  \
+        const long long n_tiles = (M + D2_WARPS * 4 * QV - 1) / (D2_WARPS * 4 * QV);                                      \
+        const unsigned g2 = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());                                      \
+        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_distortion_tiled<CPLV, QV, NSTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        k_distortion_tiled<CPLV, QV, NSTV><<<g2, D2_THREADS, smem2, st>>>(X, xnorm, M, (int)x_pitch, n_runs, run_k, run_crow0, cent, \
+                                                                          cnorm, labels, (long long*)state, kmax);       \
     } while (0)
-            if (x_pitch <= 128) LEIDA_D2(4);
-            else if (x_pitch <= 256) LEIDA_D2(8);
-            else if (x_pitch <= 416) LEIDA_D2(13);
-            else LEIDA_D2(16);
+#define LEIDA_D2N(CPLV, QV)                                                                                               \
+    do {                                                                                                                  \
+        if (nst == 4) LEIDA_D2(CPLV, QV, 4); else if (nst == 3) LEIDA_D2(CPLV, QV, 3); else LEIDA_D2(CPLV, QV, 2);        \
+    } while (0)
+            if (x_pitch <= 128) LEIDA_D2N(4, 3);             // narrow rows: three quads per warp (144 rows per tile)
+            else if (x_pitch <= 256) LEIDA_D2N(8, 2);
+            else if (x_pitch <= 416) LEIDA_D2N(13, 1);
+            else LEIDA_D2N(16, 1);
+#undef LEIDA_D2N
 #undef LEIDA_D2
             return check_launch("k_distortion_tiled", 2);
         }

@@ -31,6 +31,8 @@ SIGNATURES = {
     "leida_last_error": (c_char_p, []),
     "leida_device_sm_count": (c_int, []),
     "leida_launch_count": (c_int64, []),
+    "leida_clean_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "leida_clean_signals_f64": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, c_int, c_int, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "leida_hilbert_workspace_bytes": (c_size_t, [c_int]),
     "leida_hilbert_phase_f64": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, c_int, c_int, _P, c_size_t, _P]),
     "leida_phase_coherence_f64": (c_int, [_P, c_int, c_int, c_int64, _P, _P]),

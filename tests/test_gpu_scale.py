@@ -188,3 +188,48 @@ def test_unnormalised_rows_are_scaled_into_range(P, O):
         # the oracle's centroids carry the rounding noise of numpy's sequential float32 sums
         assert np.allclose(km.cluster_centers_, ref.cluster_centers_, rtol=0, atol=2e-6 * np.abs(ref.cluster_centers_).max()), amp
         assert km.inertia_ == pytest.approx(float(ref.inertia_), rel=1e-6)
+
+
+@pytest.mark.parametrize("opts", [
+    dict(detrend=True, standardize="zscore", filter_type="butterworth", low_pass=0.1, high_pass=0.01, TR=0.72),
+    dict(detrend=True, standardize="psc", filter_type="butterworth", low_pass=0.08, high_pass=None, TR=2.0),
+    dict(detrend=False, standardize=False, filter_type="butterworth", low_pass=None, high_pass=0.02, TR=1.0),
+    dict(detrend=True, standardize="zscore", filter_type=None, low_pass=None, high_pass=None, TR=None),
+    dict(detrend=False, standardize="zscore", filter_type=None, low_pass=None, high_pass=None, TR=None),
+])
+def test_clean_signals_vs_oracle(P, O, opts):
+    """clean_signals (signal_tools/_signal_tools.py:66-133 -> nilearn.signal.clean 0.9.1) against the oracle's
+    restatement, which runs the real scipy.signal.filtfilt.  Parity with nilearn itself is unpinned (not installed)."""
+    rng = np.random.default_rng(4)
+    t = np.arange(400)
+    sig = {"a": 100 + 3 * rng.standard_normal((7, 400)) + 0.01 * t + 2 * np.sin(2 * np.pi * 0.03 * t),
+           "b": 50 + rng.standard_normal((7, 400)), "c": 10 + rng.standard_normal((5, 150)) - 0.02 * np.arange(150)}
+    got = P.signal_tools.clean_signals(sig, **opts)
+    ref = O.clean_signals(sig, **opts)
+    assert list(got.keys()) == list(sig.keys())
+    for s in sig:
+        assert got[s].shape == sig[s].shape and got[s].dtype == np.float64
+        scale = max(1.0, float(np.abs(ref[s]).max()))
+        assert np.abs(got[s] - ref[s]).max() <= 1e-8 * scale, (s, np.abs(got[s] - ref[s]).max())
+
+
+def test_clean_signals_errors_and_pipeline(P, O):
+    with pytest.raises(ValueError):
+        P.signal_tools.clean_signals([1, 2, 3])
+    x = {"s": np.random.default_rng(0).standard_normal((3, 200))}
+    with pytest.raises(ValueError):
+        P.signal_tools.clean_signals(x, filter_type="butterworth", low_pass=0.01, high_pass=0.1, TR=1.0)
+    with pytest.raises(ValueError):
+        P.signal_tools.clean_signals(x, filter_type="butterworth", low_pass=0.1, TR=None)
+    with pytest.raises(ValueError):
+        P.signal_tools.clean_signals({"s": x["s"][:, :20]}, filter_type="butterworth", low_pass=0.1, high_pass=0.01, TR=1.0)
+    # band-limited signals through the phase -> eigenvector path: same eigenvectors as the oracle on the oracle-cleaned series
+    from pyleida import synthetic
+    ts, _ = synthetic.make_dataset(3, 12, 220, "states")
+    kw = dict(detrend=True, standardize="zscore", filter_type="butterworth", low_pass=0.1, high_pass=0.01, TR=0.72)
+    cg = P.signal_tools.clean_signals(ts, **kw)
+    co = O.clean_signals(ts, **kw)
+    for s in ts:
+        lei, _ = P.signal_tools.leading_eigenvectors(cg[s])
+        ref = O.leading_eigvec_rank2(O.hilbert_phase(co[s]))
+        assert np.abs(lei - ref).max() <= 1e-6
