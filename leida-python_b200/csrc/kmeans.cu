@@ -856,6 +856,17 @@ k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm
         int lab_cur = lab_lane ? lab_ptr[0] : 0;
         int lab_n1 = (lab_lane && 1 < n_runs) ? lab_ptr[(long long)M] : 0;
         int lab_n2 = (lab_lane && 2 < n_runs) ? lab_ptr[2 * (long long)M] : 0;
+        const bool b4 = lane & 16, b3 = lane & 8;
+        const int u_mine = (b4 ? 2 : 0) + (b3 ? 1 : 0);          // the row of a quad this lane finishes
+        double xn_q[Q], pend[Q], pend_cn[Q];
+#pragma unroll
+        for (int qd = 0; qd < Q; ++qd) {
+            xn_q[qd] = xn[4 * qd];
+#pragma unroll
+            for (int u = 1; u < 4; ++u) if (u_mine == u) xn_q[qd] = xn[4 * qd + u];
+            pend[qd] = 0.0;
+            pend_cn[qd] = 1.0;
+        }
         __syncthreads();                       // the previous tile's last compute is done: the ring may be refilled
 #pragma unroll
         for (int r = 0; r < NST - 1; ++r) stage(r);
@@ -866,7 +877,6 @@ k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm
             stage(r + NST - 1);                // refills the buffer run r - 1 used
             const int lab_n3 = (lab_lane && r + 3 < n_runs) ? lab_ptr[(long long)(r + 3) * M] : 0;
             const float* cb = cbuf + (size_t)b * kmax * XP;
-            unsigned long long hi = 0, lo = 0;
 #pragma unroll
             for (int qd = 0; qd < Q; ++qd) {
                 int l[4];
@@ -896,8 +906,8 @@ k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm
                         }
                     }
                 }
-                // four sums over 32 lanes with 6 shuffles: halve the values held per lane twice, then a plain butterfly
-                const bool b4 = lane & 16, b3 = lane & 8;
+                // four sums over 32 lanes with 6 shuffles: halve the values held per lane twice, then a plain butterfly;
+                // afterwards the 8 lanes with the same (bit 4, bit 3) all hold the sum of row u_mine of the quad
                 double a0 = b4 ? s[2] : s[0], a1 = b4 ? s[3] : s[1];
                 a0 += __shfl_xor_sync(0xffffffffu, b4 ? s[0] : s[2], 16);
                 a1 += __shfl_xor_sync(0xffffffffu, b4 ? s[1] : s[3], 16);
@@ -906,30 +916,39 @@ k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm
                 t += __shfl_xor_sync(0xffffffffu, t, 4);
                 t += __shfl_xor_sync(0xffffffffu, t, 2);
                 t += __shfl_xor_sync(0xffffffffu, t, 1);
-                // lanes 0, 8, 16, 24 finish rows 0, 1, 2, 3 of the quad
-                const int u_mine = (b4 ? 2 : 0) + (b3 ? 1 : 0);
-                double xn_mine = xn[4 * qd];
+                // lane (row u_mine, slot r & 7) keeps the dot product and the centroid norm: the division, the squaring
+                // and the exact-integer conversion are done for eight runs at a time with all 32 lanes busy
+                int l_mine = l[0];
 #pragma unroll
-                for (int u = 1; u < 4; ++u) if (u_mine == u) xn_mine = xn[4 * qd + u];
-                if ((lane & 7) == 0 && row0 + 4 * qd + u_mine < M) {
-                    const double d = cosine_distance(t, xn_mine, cnb[b * kmax + l[u_mine]]);
-                    const double d2 = d * d * kFracScale;   // exact scaling
-                    if (d2 == d2) {
-                        const double f = floor(d2);
-                        hi += (unsigned long long)(long long)f;
-                        lo += (unsigned long long)(long long)floor((d2 - f) * kFracScale);
-                    } else {
-                        hi += 0x4000000000000000ULL;        // poison: NaN distance
+                for (int u = 1; u < 4; ++u) if (u_mine == u) l_mine = l[u];
+                const double cn_mine = cnb[b * kmax + l_mine];
+                if ((lane & 7) == (r & 7)) { pend[qd] = t; pend_cn[qd] = cn_mine; }
+            }
+            if ((r & 7) == 7 || r == n_runs - 1) {
+                const int my_run = (r & ~7) + (lane & 7);
+                unsigned long long hi = 0, lo = 0;
+#pragma unroll
+                for (int qd = 0; qd < Q; ++qd) {
+                    if (my_run <= r && row0 + 4 * qd + u_mine < M) {
+                        const double d = cosine_distance(pend[qd], xn_q[qd], pend_cn[qd]);
+                        const double d2 = d * d * kFracScale;   // exact scaling
+                        if (d2 == d2) {
+                            const double f = floor(d2);
+                            hi += (unsigned long long)(long long)f;
+                            lo += (unsigned long long)(long long)floor((d2 - f) * kFracScale);
+                        } else {
+                            hi += 0x4000000000000000ULL;        // poison: NaN distance
+                        }
                     }
                 }
-            }
-            hi += __shfl_xor_sync(0xffffffffu, hi, 8);
-            lo += __shfl_xor_sync(0xffffffffu, lo, 8);
-            hi += __shfl_xor_sync(0xffffffffu, hi, 16);
-            lo += __shfl_xor_sync(0xffffffffu, lo, 16);
-            if (lane == 0 && (hi | lo)) {
-                atomicAdd(&s_hi[r], hi);
-                atomicAdd(&s_lo[r], lo);
+                hi += __shfl_xor_sync(0xffffffffu, hi, 8);
+                lo += __shfl_xor_sync(0xffffffffu, lo, 8);
+                hi += __shfl_xor_sync(0xffffffffu, hi, 16);
+                lo += __shfl_xor_sync(0xffffffffu, lo, 16);
+                if (lane < 8 && my_run <= r && (hi | lo)) {
+                    atomicAdd(&s_hi[my_run], hi);
+                    atomicAdd(&s_lo[my_run], lo);
+                }
             }
             lab_cur = lab_n1; lab_n1 = lab_n2; lab_n2 = lab_n3;
         }

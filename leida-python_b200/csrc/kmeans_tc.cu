@@ -577,37 +577,53 @@ __device__ __forceinline__ long long quant40(float v) { return __double2ll_rn((d
 // is 0x4B400000 + the integer.  The bit patterns are summed as they are in 32-bit wrap-around arithmetic and
 // the offsets removed every 512 elements (|sum h| <= 2^29).  Same integers as quant40 (checked exhaustively
 // enough on the host: 2e8 random bit patterns and the tie / denormal / +-1 edge cases).
+// Four adjacent columns per thread (one 16-byte gather per listed row: a quarter of the row-index reads, address
+// products and load instructions of a column-per-thread loop -- the kernel is bound by instruction issue).
+// out[c] += sum over the listed rows of quant40(x[row][j4 + c]); elements 1 and 3 of every load take the FMA-pipe path
+// when UNIT.
 template <bool UNIT>
-__device__ __forceinline__ long long quant_sum(const float* __restrict__ xb, unsigned j, unsigned XP,
-                                               const unsigned short* __restrict__ rows, int e0, int e1, int stride) {
+__device__ __forceinline__ void quant_sum4(const float* __restrict__ xb, unsigned j4, unsigned XP,
+                                           const unsigned short* __restrict__ rows, int e0, int e1, int stride,
+                                           long long* out) {
     constexpr float MAGIC = 12582912.f;           // 1.5 * 2^23
     constexpr uint32_t MAGIC_BITS = 0x4B400000u;
-    long long total = 0;
+    auto fma_path = [&](float x, uint32_t& sh, uint32_t& sl) {
+        const float th = fmaf(x, 1048576.f, MAGIC);                 // MAGIC + h
+        const float r = fmaf(th - MAGIC, -9.5367431640625e-07f, x); // x - h * 2^-20
+        const float tl = fmaf(r, 1099511627776.f, MAGIC);           // MAGIC + rne(r * 2^40)
+        sh += __float_as_uint(th);
+        sl += __float_as_uint(tl);
+    };
     int e = e0;
-    while (e + 7 * stride < e1) {
-        uint32_t sh = 0, sl = 0, nb = 0;
-        for (; nb < 128 && e + 7 * stride < e1; ++nb, e += 8 * stride) {
-            float v[8];
+    while (e + 3 * stride < e1) {
+        uint32_t sh1 = 0, sl1 = 0, sh3 = 0, sl3 = 0, nb = 0;
+        for (; nb < 128 && e + 3 * stride < e1; ++nb, e += 4 * stride) {
+            float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldg(xb + ((unsigned)rows[e + u * stride] * XP + j));
+            for (int u = 0; u < 4; ++u)
+                v[u] = __ldg(reinterpret_cast<const float4*>(xb + ((unsigned)rows[e + u * stride] * XP + j4)));
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (UNIT && (u & 1)) {
-                    const float th = fmaf(v[u], 1048576.f, MAGIC);                 // MAGIC + h
-                    const float r = fmaf(th - MAGIC, -9.5367431640625e-07f, v[u]); // x - h * 2^-20
-                    const float tl = fmaf(r, 1099511627776.f, MAGIC);              // MAGIC + rne(r * 2^40)
-                    sh += __float_as_uint(th);
-                    sl += __float_as_uint(tl);
+            for (int u = 0; u < 4; ++u) {
+                out[0] += quant40(v[u].x);
+                out[2] += quant40(v[u].z);
+                if (UNIT) {
+                    fma_path(v[u].y, sh1, sl1);
+                    fma_path(v[u].w, sh3, sl3);
                 } else {
-                    total += quant40(v[u]);
+                    out[1] += quant40(v[u].y);
+                    out[3] += quant40(v[u].w);
                 }
             }
         }
-        if (UNIT)
-            total += ((long long)(int)(sh - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl - 4u * nb * MAGIC_BITS);
+        if (UNIT) {          // 4 * nb elements per column were summed with the offset in place (|sum h| <= 2^29)
+            out[1] += ((long long)(int)(sh1 - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl1 - 4u * nb * MAGIC_BITS);
+            out[3] += ((long long)(int)(sh3 - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl3 - 4u * nb * MAGIC_BITS);
+        }
     }
-    for (; e < e1; e += stride) total += quant40(__ldg(xb + ((unsigned)rows[e] * XP + j)));
-    return total;
+    for (; e < e1; e += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((unsigned)rows[e] * XP + j4)));
+        out[0] += quant40(v.x); out[1] += quant40(v.y); out[2] += quant40(v.z); out[3] += quant40(v.w);
+    }
 }
 
 template <bool UNIT>
@@ -702,7 +718,9 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
         if (o != 0xff) s_out[atomicAdd(&s_pout[o], 1)] = (unsigned short)(v & 0xffff);
     }
     __syncthreads();
-    const int CW = N >= APPLY_THREADS ? APPLY_THREADS : ((N + 31) & ~31);
+    // thread (g, j4): columns 4 j4 .. 4 j4 + 3 of its share (rows g, g + groups, ...) of every cluster's lists
+    const int C4 = (N + 3) >> 2;                                   // float4 columns (pad columns of X are zero)
+    const int CW = C4 >= APPLY_THREADS ? APPLY_THREADS : ((C4 + 31) & ~31);
     const int groups = APPLY_THREADS / CW;
     const int g = threadIdx.x / CW, j0 = threadIdx.x - g * CW;
     if (g < groups) {
@@ -711,11 +729,17 @@ k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int3
         for (int k = 0; k < K; ++k) {
             const int ib = s_cin[k], ie = s_cin[k + 1], ob = s_cout[k], oe = s_cout[k + 1];
             if (ib == ie && ob == oe) continue;
-            for (int j = j0; j < N; j += CW) {
-                const long long sum = quant_sum<UNIT>(xb, (unsigned)j, (unsigned)XP, s_in, ib + g, ie, groups) -
-                                      quant_sum<UNIT>(xb, (unsigned)j, (unsigned)XP, s_out, ob + g, oe, groups);
-                if (sum != 0)
-                    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + k) * AP + j), (unsigned long long)sum);
+            for (int j4 = j0; j4 < C4; j4 += CW) {
+                long long sin4[4] = {0, 0, 0, 0}, sout4[4] = {0, 0, 0, 0};
+                quant_sum4<UNIT>(xb, (unsigned)(4 * j4), (unsigned)XP, s_in, ib + g, ie, groups, sin4);
+                quant_sum4<UNIT>(xb, (unsigned)(4 * j4), (unsigned)XP, s_out, ob + g, oe, groups, sout4);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const long long sum = sin4[c] - sout4[c];
+                    if (sum != 0)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(acc + (long long)(crow0 + k) * AP + 4 * j4 + c),
+                                  (unsigned long long)sum);
+                }
             }
         }
     }

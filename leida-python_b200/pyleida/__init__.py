@@ -5,6 +5,7 @@ sm_100a CUDA kernels in libleida_b200.so.  No CPU fallback."""
 from . import _native  # noqa: F401  (fails loudly when the CUDA library is missing)
 from . import signal_tools, clustering, dynamics_metrics, stats  # noqa: F401
 from ._leida import Leida
+from ._data_loader import DataLoader
 
-__all__ = ["Leida", "signal_tools", "clustering", "dynamics_metrics", "stats"]
+__all__ = ["Leida", "DataLoader", "signal_tools", "clustering", "dynamics_metrics", "stats"]
 __version__ = "0.1.0"

@@ -120,8 +120,12 @@ class Leida:
             raise TypeError("'n_perm' must be an integer!")
         if n_perm < 100:
             raise ValueError("The number of permutations cannot be lower than 100.")
-        if not isinstance(save_results, bool):
+        if not isinstance(save_results, bool) and save_results not in ("binary", "fast"):
             raise TypeError("'save_results' must be a boolean value (True or False)!")
+        # "binary": the reference's folder plus .npy copies of the two volume-sized tables; "fast": the .npy copies
+        # INSTEAD of the two big csv files (see results_io.py)
+        save_binary, save_csv = save_results in ("binary", "fast"), save_results != "fast"
+        save_results = bool(save_results)
         self._results_path_ = "LEiDA_results"
         if save_results:
             if os.path.exists(self._results_path_):                                        # _leida.py:256-260
@@ -136,8 +140,9 @@ class Leida:
         self._run_stats(stats, paired_tests, n_perm, random_state)
         if save_results:                                                                   # _leida.py:306-310 and the stage writers
             from .results_io import save_clustering, save_dynamics, save_eigenvectors
-            save_eigenvectors(self._results_path_, self.eigenvectors)
-            save_clustering(self._results_path_, self.predictions, self._clustering_.performance, self._clustering_.models)
+            save_eigenvectors(self._results_path_, self.eigenvectors, binary=save_binary, csv=save_csv)
+            save_clustering(self._results_path_, self.predictions, self._clustering_.performance, self._clustering_.models,
+                            binary=save_binary, csv=save_csv)
             save_dynamics(self._results_path_, {"occupancies": self._dynamics_.occupancies,
                                                 "dwell_times": self._dynamics_.dwell_times,
                                                 "transitions": self._dynamics_.transitions})

@@ -604,6 +604,10 @@ class KMeansLeida:
         return eng.predict(self.cluster_centers_).cpu().numpy().astype(np.int64)
 
 
+# pickles of fitted models name the reference's module path (see clustering/_clustering.py in this package)
+KMeansLeida.__module__ = "pyleida.clustering._clustering"
+
+
 def score_sample(M, drawn=None, comm=None):
     """Rows scored by Dunn / silhouette: all of them up to 30 000, else the reference's 30 000-row random
     sub-sample (clustering/_clustering.py:318-320) -- `drawn` when the draw was already made.  With several ranks the

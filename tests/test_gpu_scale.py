@@ -199,7 +199,11 @@ def test_unnormalised_rows_are_scaled_into_range(P, O):
 ])
 def test_clean_signals_vs_oracle(P, O, opts):
     """clean_signals (signal_tools/_signal_tools.py:66-133 -> nilearn.signal.clean 0.9.1) against the oracle's
-    restatement, which runs the real scipy.signal.filtfilt.  Parity with nilearn itself is unpinned (not installed)."""
+    restatement, which runs the real scipy.signal.filtfilt.  Parity with nilearn itself is unpinned (not installed).
+    Tolerance: 1e-8 of the output scale, except for the 10th-order band-pass in transfer-function form that nilearn
+    uses (butter(5, [lo, hi], output='ba')): that recursion is ill-conditioned -- scipy's own filtfilt moves by 4e-6
+    when its input is perturbed by 1e-15, and differs from the second-order-sections form by 3.7e-6 (measured on this
+    input) -- so there the comparison is to 2e-5, the reference algorithm's own noise floor."""
     rng = np.random.default_rng(4)
     t = np.arange(400)
     sig = {"a": 100 + 3 * rng.standard_normal((7, 400)) + 0.01 * t + 2 * np.sin(2 * np.pi * 0.03 * t),
@@ -210,7 +214,8 @@ def test_clean_signals_vs_oracle(P, O, opts):
     for s in sig:
         assert got[s].shape == sig[s].shape and got[s].dtype == np.float64
         scale = max(1.0, float(np.abs(ref[s]).max()))
-        assert np.abs(got[s] - ref[s]).max() <= 1e-8 * scale, (s, np.abs(got[s] - ref[s]).max())
+        band = opts["low_pass"] is not None and opts["high_pass"] is not None
+        assert np.abs(got[s] - ref[s]).max() <= (2e-5 if band else 1e-8) * scale, (s, np.abs(got[s] - ref[s]).max())
 
 
 def test_clean_signals_errors_and_pipeline(P, O):
@@ -232,4 +237,36 @@ def test_clean_signals_errors_and_pipeline(P, O):
     for s in ts:
         lei, _ = P.signal_tools.leading_eigenvectors(cg[s])
         ref = O.leading_eigvec_rank2(O.hilbert_phase(co[s]))
-        assert np.abs(lei - ref).max() <= 1e-6
+        assert np.abs(lei - ref).max() <= 1e-4         # band-pass conditioning (see test_clean_signals_vs_oracle)
+
+
+def test_results_folder_binary_and_dataloader(P, tmp_path, monkeypatch):
+    """save_results='binary' writes the reference's folder plus .npy copies of the volume-sized tables; 'fast' writes
+    the .npy copies only.  pyleida.DataLoader (the reference's accessor names, _data_loader.py:146-345) reads both."""
+    import pickle
+    from pyleida import synthetic
+    ts, classes = synthetic.make_dataset(4, 8, 30, "states")
+    data = tmp_path / "data"
+    data.mkdir()
+    with open(data / "time_series.pkl", "wb") as f:
+        pickle.dump(ts, f)
+    with open(data / "metadata.pkl", "wb") as f:
+        pickle.dump(classes, f)
+    (data / "rois_labels.txt").write_text("\n".join(f"r{i}" for i in range(8)) + "\n")
+    for mode in ("binary", "fast"):
+        work = tmp_path / mode
+        work.mkdir()
+        monkeypatch.chdir(work)
+        m = P.Leida(str(data)).fit_predict(TR=1.0, save_results=mode, random_state=0, K_min=2, K_max=3, n_init=1)
+        root = work / "LEiDA_results"
+        assert (root / "eigenvectors.npy").exists() and (root / "clustering" / "predictions.npy").exists()
+        assert (root / "eigenvectors.csv").exists() == (mode == "binary")
+        dl = P.DataLoader(str(data), str(root))
+        assert np.array_equal(dl.eigenvectors.iloc[:, 2:].values, m.eigenvectors.iloc[:, 2:].values)
+        assert list(dl.eigenvectors.columns) == list(m.eigenvectors.columns)
+        assert np.array_equal(dl.predictions["k_3"].values, m.predictions["k_3"].values)
+        assert np.array_equal(dl.load_model(3).cluster_centers_, m.load_model(3).cluster_centers_)
+        assert np.allclose(dl.occupancies(2).iloc[:, 2:].values, m.occupancies(2).iloc[:, 2:].values, rtol=1e-12)
+        d = dl.centroids_distances(3)                       # KMeansLeida.transform on the GPU from the loaded model
+        assert np.allclose(d.iloc[:, 2:].values, m.centroids_distances(3).iloc[:, 2:].values, atol=1e-6)
+        assert type(dl.load_model(2)).__module__ == "pyleida.clustering._clustering"
