@@ -520,9 +520,12 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
         f0.record()
         t_wall = time.perf_counter()
         h2d = d2h = 0
+        phases = {}
         for _ in range(n_e2e):
             m = step_e2e()
             h2d, d2h = int(m.h2d_bytes), int(m.d2h_bytes)
+            for kk, vv in getattr(m, "timings_", {}).items():
+                phases[kk] = phases.get(kk, 0.0) + vv / n_e2e
             del m
         f1.record()
         barrier()
@@ -536,6 +539,7 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
         e2e = {"value": M_global * n_e2e / (float(te[0].item()) * 1e-3), "unit": "volumes/s",
                "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()), "steps": n_e2e,
                "ms_per_step": float(te[0].item()) / n_e2e,
+               "host_phases_ms_rank0": {kk: round(vv, 1) for kk, vv in phases.items()},
                "call": "Leida.from_arrays(ts, classes).fit_predict(..., scores=False, stats=False) + the three metric tables "
                        "of every K: the metric is phase->eigvec->k-means->metrics (SURVEY 8d); quality scores and "
                        "permutation tests are separate stages"}
@@ -563,7 +567,7 @@ def native_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     key, wl = args.config, WORKLOADS[args.config]
-    r = measure(torch, dist, args, key, wl, args.steps, args.warmup)
+    r = measure(torch, dist, args, key, wl, args.steps, args.warmup, with_e2e=not args.no_e2e)
     out = None
     if rank == 0:
         out = {
@@ -630,6 +634,7 @@ def main():
     ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 secondary measurement")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host API) leg: profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

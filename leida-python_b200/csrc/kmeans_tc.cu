@@ -579,8 +579,7 @@ __device__ __forceinline__ long long quant40(float v) { return __double2ll_rn((d
 // enough on the host: 2e8 random bit patterns and the tie / denormal / +-1 edge cases).
 // Four adjacent columns per thread (one 16-byte gather per listed row: a quarter of the row-index reads, address
 // products and load instructions of a column-per-thread loop -- the kernel is bound by instruction issue).
-// out[c] += sum over the listed rows of quant40(x[row][j4 + c]); elements 1 and 3 of every load take the FMA-pipe path
-// when UNIT.
+// out[c] += sum over the listed rows of quant40(x[row][j4 + c]); when UNIT every element takes the FMA-pipe path.
 template <bool UNIT>
 __device__ __forceinline__ void quant_sum4(const float* __restrict__ xb, unsigned j4, unsigned XP,
                                            const unsigned short* __restrict__ rows, int e0, int e1, int stride,
@@ -596,7 +595,7 @@ __device__ __forceinline__ void quant_sum4(const float* __restrict__ xb, unsigne
     };
     int e = e0;
     while (e + 3 * stride < e1) {
-        uint32_t sh1 = 0, sl1 = 0, sh3 = 0, sl3 = 0, nb = 0;
+        uint32_t sh[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0}, nb = 0;
         for (; nb < 128 && e + 3 * stride < e1; ++nb, e += 4 * stride) {
             float4 v[4];
 #pragma unroll
@@ -604,20 +603,25 @@ __device__ __forceinline__ void quant_sum4(const float* __restrict__ xb, unsigne
                 v[u] = __ldg(reinterpret_cast<const float4*>(xb + ((unsigned)rows[e + u * stride] * XP + j4)));
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                out[0] += quant40(v[u].x);
-                out[2] += quant40(v[u].z);
                 if (UNIT) {
-                    fma_path(v[u].y, sh1, sl1);
-                    fma_path(v[u].w, sh3, sl3);
+                    // all four on the FMA pipe: with 16-byte gathers the conversion pipe (F2F + F2I.S64, 16 lanes per
+                    // clock and SM) was what bound the dense passes when half of the elements still went through it
+                    fma_path(v[u].x, sh[0], sl[0]);
+                    fma_path(v[u].y, sh[1], sl[1]);
+                    fma_path(v[u].z, sh[2], sl[2]);
+                    fma_path(v[u].w, sh[3], sl[3]);
                 } else {
+                    out[0] += quant40(v[u].x);
                     out[1] += quant40(v[u].y);
+                    out[2] += quant40(v[u].z);
                     out[3] += quant40(v[u].w);
                 }
             }
         }
         if (UNIT) {          // 4 * nb elements per column were summed with the offset in place (|sum h| <= 2^29)
-            out[1] += ((long long)(int)(sh1 - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl1 - 4u * nb * MAGIC_BITS);
-            out[3] += ((long long)(int)(sh3 - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl3 - 4u * nb * MAGIC_BITS);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                out[c] += ((long long)(int)(sh[c] - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl[c] - 4u * nb * MAGIC_BITS);
         }
     }
     for (; e < e1; e += stride) {
@@ -627,7 +631,7 @@ __device__ __forceinline__ void quant_sum4(const float* __restrict__ xb, unsigne
 }
 
 template <bool UNIT>
-__global__ void __launch_bounds__(APPLY_THREADS)
+__global__ void __launch_bounds__(APPLY_THREADS, 3)
 k_diff_apply(const float* __restrict__ X, long long M, int N, int XP, const int32_t* __restrict__ plan,
              const int32_t* __restrict__ prun, const int32_t* __restrict__ run_k,
              const int32_t* __restrict__ run_crow0, int32_t* __restrict__ labels_cur,

@@ -163,6 +163,14 @@ class Leida:
         if min(n_vols) < 1:
             raise Exception("every subject needs at least 3 volumes")
         self.h2d_bytes = self.d2h_bytes = 0
+        import time
+        t_mark = [time.perf_counter()]
+        self.timings_ = {}
+
+        def mark(name):
+            t = time.perf_counter()
+            self.timings_[name] = self.timings_.get(name, 0.0) + 1e3 * (t - t_mark[0])
+            t_mark[0] = t
         # host -> device: consecutive subjects with the same T are staged as one pinned block
         blocks, i = [], 0
         while i < len(ids):
@@ -205,6 +213,7 @@ class Leida:
             cond_list = np.repeat(np.asarray(conds, dtype=object), n_vols)
             segments = Segments.contiguous(np.asarray(ids), np.asarray(conds), n_vols)
         self._meta = (sub_list, cond_list)
+        mark("stage_inputs_h2d_ms")
         seg_off = torch.from_numpy(segments.off).to(dev)
         seg_rows = torch.from_numpy(segments.rows).to(dev)
         self.h2d_bytes += segments.off.nbytes + segments.rows.nbytes
@@ -231,6 +240,7 @@ class Leida:
                          f64_sink=early_eigenvectors if keep_eigenvectors else None)
         self.device_result_ = res
         self.kmeans_batch_ = res.batch
+        mark("device_pipeline_ms")
         # device -> host: labels (as the int64 the reference's frames hold, in both orientations: per-K rows for
         # the models, per-volume rows for the predictions frame), centroids, integer metric tables
         ks = list(range(self._K_min_, self._K_max_ + 1))
@@ -242,6 +252,7 @@ class Leida:
         torch.cuda.current_stream().synchronize()
         if side is not None:
             side.synchronize()
+        mark("d2h_results_ms")
         labels, labels_t = pinned["labels"].numpy(), pinned["labels_t"].numpy()
         occ, runs, trans = pinned["occ"].numpy(), pinned["runs"].numpy(), pinned["trans"].numpy()
         self.d2h_bytes += labels.nbytes + labels_t.nbytes + occ.nbytes + runs.nbytes + trans.nbytes
@@ -281,6 +292,7 @@ class Leida:
                 for c in (self.classes[s_][1:nv_ + 1] if len(self.classes[s_]) > 1 else self.classes[s_][:1])]
         self._classes_lst_ = np.unique(np.asarray(used).astype(str)).tolist()
         self._N_classes_ = len(self._classes_lst_)
+        mark("assemble_frames_ms")
 
     def _run_stats(self, stats, paired_tests, n_perm, random_state):
         """Stage 4b of the reference (_leida.py:336-342): permutation tests per state and K.  The tables are tested as

@@ -20,6 +20,8 @@ for stage in "$@"; do
     stage12)   timeout 600 python tools/stage12_probe.py > $OUT/stage12_probe.txt 2>&1; echo "stage12 rc=$?"; cat $OUT/stage12_probe.txt ;;
     bench_dump) LEIDA_BENCH_DUMP=$OUT/per_launch.json timeout 900 python bench.py --steps 2 --warmup 2 --no-cpu --no-secondary > $OUT/bench_dump.json 2> $OUT/bench_dump.err; echo "bench_dump rc=$?" ;;
     ncu_stage12) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_hilbert|k_eigvec_rank2" -c 4 -o $OUT/stage12 -f python tools/stage12_probe.py 60 > $OUT/ncu_stage12.log 2>&1; echo "ncu_stage12 rc=$?" ;;
+    config4)   timeout 900 python bench.py --config config4 --steps 2 --warmup 1 --no-secondary > $OUT/bench_config4.json 2> $OUT/bench_config4.err; echo "config4 rc=$?"; timeout 600 python tools/config4_dense.py 3 > $OUT/config4_dense.txt 2>&1; echo "config4_dense rc=$?"; cat $OUT/config4_dense.txt ;;
+    config5)   timeout 1200 python bench.py --config config5 --steps 1 --warmup 1 --no-secondary > $OUT/bench_config5.json 2> $OUT/bench_config5.err; echo "config5 rc=$?" ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
