@@ -26,7 +26,7 @@ def _staging_pool():
         from concurrent.futures import ThreadPoolExecutor
         # several ranks on one host share its cores (torchrun exports LOCAL_WORLD_SIZE)
         per_rank = (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, per_rank)))
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(16, per_rank)))
     return _POOL
 
 
@@ -183,7 +183,7 @@ class Leida:
             dev_block = torch.empty((j - i, N, T), dtype=torch.float64, device=dev)
             # stage in slices: worker threads fill pinned memory (numpy copies release the GIL); all fills are
             # queued at once and every slice goes over PCIe as soon as its own fills are done
-            step = max(1, (j - i + 7) // 8)
+            step = max(1, (j - i + 15) // 16)
 
             def fill(lo, hi, base=i):
                 for b in range(lo, hi):

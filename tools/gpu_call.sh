@@ -22,6 +22,14 @@ for stage in "$@"; do
     ncu_stage12) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_hilbert|k_eigvec_rank2" -c 4 -o $OUT/stage12 -f python tools/stage12_probe.py 60 > $OUT/ncu_stage12.log 2>&1; echo "ncu_stage12 rc=$?" ;;
     config4)   timeout 900 python bench.py --config config4 --steps 2 --warmup 1 --no-secondary > $OUT/bench_config4.json 2> $OUT/bench_config4.err; echo "config4 rc=$?"; timeout 600 python tools/config4_dense.py 3 > $OUT/config4_dense.txt 2>&1; echo "config4_dense rc=$?"; cat $OUT/config4_dense.txt ;;
     config5)   timeout 1200 python bench.py --config config5 --steps 1 --warmup 1 --no-secondary > $OUT/bench_config5.json 2> $OUT/bench_config5.err; echo "config5 rc=$?" ;;
+    ncu_final) B="python bench.py --steps 1 --warmup 0 --no-cpu --no-secondary --no-e2e"
+               timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv $B > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?"
+               timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_tc_assign|k_recheck|k_diff_apply|k_update" -c 4 -o $OUT/pass0 -f $B > $OUT/ncu_pass0.log 2>&1; echo "ncu pass0 rc=$?"
+               timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_distortion_tiled" -c 1 -o $OUT/distortion -f $B > $OUT/ncu_dist.log 2>&1; echo "ncu distortion rc=$?"
+               timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_hilbert|k_eigvec_rank2" -c 2 -o $OUT/stage12 -f $B > $OUT/ncu_s12.log 2>&1; echo "ncu stage12 rc=$?" ;;
+    mgpu_auto) LEIDA_EXCHANGE=auto timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py > $OUT/mgpu_check_${NG}gpu_auto.log 2>&1; echo "mgpu auto rc=$?"; grep "world=" $OUT/mgpu_check_${NG}gpu_auto.log ;;
+    mbench4)   LEIDA_EXCHANGE=auto timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 3 --warmup 2 > $OUT/bench_4gpu_auto.json 2> $OUT/bench_4gpu_auto.err; echo "mbench4 rc=$?" ;;
+    mconfig5)  LEIDA_EXCHANGE=auto timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $NG --config config5 --steps 1 --warmup 1 > $OUT/bench_config5_${NG}gpu.json 2> $OUT/bench_config5_${NG}gpu.err; echo "mconfig5 rc=$?" ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
