@@ -47,13 +47,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+    long long t0 = 0;
     for (unsigned spin = 0; !done; ++spin) {
         asm volatile(
             "{\n.reg .pred P1;\n"
             "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
             "selp.b32 %0, 1, 0, P1;\n}\n"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (!done && spin > (1u << 26)) __trap();   // a lost arrival must fail loudly, not hang the GPU
+        // A lost arrival must fail loudly, not hang the GPU -- but by TIME, not by poll count: preemption, MPS
+        // time-slicing or a debugger can stretch a legitimate wait arbitrarily in polls.  ~20 s of SM clock.
+        if (!done && (spin & 0xFFFFFu) == 0xFFFFFu) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (40ll << 30)) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {

@@ -207,7 +207,14 @@ class Leida:
                 np.asarray(self.classes[s], dtype=object)[1:nv_ + 1] if len(self.classes[s]) > 1
                 else np.repeat(np.asarray(self.classes[s][:1], dtype=object), nv_)
                 for s, nv_ in zip(ids, n_vols)])
-            segments = Segments.from_arrays(sub_list.astype(str), cond_list.astype(str))
+            # ids keep their own dtype (np.unique of integer ids sorts 2 before 10, like the reference's
+            # np.unique(metadata.subject_id)); only mixed-type ids fall back to their string form
+            try:
+                sub_native = np.repeat(np.asarray(ids), n_vols)
+                np.unique(sub_native)
+            except TypeError:
+                sub_native = sub_list.astype(str)
+            segments = Segments.from_arrays(sub_native, cond_list.astype(str))
         else:
             conds = [self.classes[s][0] for s in ids]
             cond_list = np.repeat(np.asarray(conds, dtype=object), n_vols)

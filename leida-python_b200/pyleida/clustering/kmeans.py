@@ -201,6 +201,10 @@ class KMeansEngine:
             e1.record()
             profile.setdefault(name, []).append((e0, e1))
 
+        if assign == "tc" and R > 4096:
+            # the tensor-core packing plan holds at most 4096 runs per batch (kmeans_tc.cu: PLAN_MAX_RUNS)
+            warnings.warn(f"{R} runs in one batch exceed the tensor-core plan's 4096: using the CUDA-core assignment")
+            assign = "simt"
         tc = assign == "tc"
         # trust threshold of the tensor-core argmax: the library's measured bound, optionally scaled (experiments only)
         tau = float(nv.lib.leida_kmeans_tc_tau(self.N)) * float(os.environ.get("LEIDA_TC_TAU_SCALE", "1"))
