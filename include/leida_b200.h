@@ -282,6 +282,25 @@ int leida_kmeans_exchange_publish(int n_runs, const int32_t* run_k, const int32_
                                   const int64_t* local_words, int64_t n_acc_words, int64_t* exchange_half,
                                   uint64_t* const* peer_flags, int n_peers, int my_rank, uint64_t* seq,
                                   int32_t* counter, leida_stream_t stream);
+/* The same update with the exchange fused in and the centroid rows kept in registers from the sums to the packed
+ * tensor-core operands (the form the engine uses; x_pitch <= 1024).  local_words: this rank's acc words followed, from
+ * word state_offset_words, by its state words (the buffer leida_kmeans_tc_apply accumulates into).
+ * Single GPU: exchange_half = NULL (the other exchange arguments are ignored).
+ * Several GPUs of one node: exchange_half = this rank's half (of this pass's parity) of its symmetric-memory buffer,
+ * peer_halves = DEVICE array of every rank's pointer to that half, multicast_half = multicast address of the half or
+ * NULL, peer_flags = DEVICE array of every rank's flag array ([n_peers][flag_pitch] uint64, zero at start),
+ * flags_local = this rank's own flag array, seq = device uint64 pass counter (zero at start, same on every rank).
+ * The CTA of run r publishes the run's words, stores ++pass into flag[my_rank][r] of every rank (release, system
+ * scope), waits until flag[*][r] of every rank has reached it, and reads every word as the sum over ranks -- one
+ * multimem.ld_reduce.add.u64 through the NVSwitch multicast mapping, or one load per rank.  Halves must alternate
+ * from pass to pass.  No separate publish call, no collective, no host involvement. */
+int leida_kmeans_update_fused(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                              int64_t* local_words, int64_t state_offset_words, int64_t* exchange_half,
+                              const int64_t* const* peer_halves, const int64_t* multicast_half,
+                              uint64_t* const* peer_flags, const uint64_t* flags_local, int64_t flag_pitch,
+                              int n_peers, int my_rank, uint64_t* seq, float* cent, double* cnorm,
+                              int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol,
+                              void* C1, void* C2, int32_t* mailbox, leida_stream_t stream);
 /* n_active_out: device int32[8], zeroed once by the caller ([0],[1] scratch re-armed by the kernel,
  * [2] = runs still active after this call, [3] = calls completed, [4] = first all-stopped call).  mailbox (may be NULL): HOST-visible (pinned, mapped),
  * 8-byte aligned; the last CTA publishes ONE 64-bit word there -- bits 0-15 runs still active, bits 16-39 number

@@ -680,6 +680,202 @@ k_update(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restric
     }
 }
 
+// Control + centroid update, second form: the exchange with the other GPUs and the whole update of a run happen in ONE
+// kernel and the centroid rows never leave registers between the sums and the packed tensor-core operands.
+//   * exchange (several GPUs): the CTA of run r copies the run's acc rows + state words into this pass's half of the
+//     rank's symmetric buffer, raises flag[my_rank][r] = pass number on every rank (one system fence, release stores),
+//     and waits for flag[*][r] of all ranks.  Per-run flags: no grid-wide ticket, no separate publish launch, and a run
+//     is held up only by its own counterparts.  Every word is then read as the sum over ranks (multimem.ld_reduce
+//     through the multicast mapping, else one load per rank).
+//   * update: a warp owns whole centroid rows: its lanes hold the row's sums (all loads of a row in flight together),
+//     form the means, reduce the norm with shuffles (same summation order as cent_norm_warp) and write the float32
+//     centroid, the norm and the unit-normalised bf16 hi/lo operands straight from registers: one round trip to memory
+//     instead of four dependent ones.
+// Padding rows / columns of a slot are constant after leida_kmeans_tc_plan(pack = 1) and are not rewritten; a run
+// that stops keeps its last operands until the next re-plan (its labels are ignored from then on).
+struct ExchangeParams {
+    long long* my_half;                       // null: single GPU (sums are read from acc / state directly)
+    const long long* const* peers;            // every rank's half of this pass
+    const long long* mc;                      // multicast address of the half, or null
+    unsigned long long* const* peer_flags;    // every rank's flag array, [n_ranks][flag_pitch]
+    const unsigned long long* flags_local;
+    unsigned long long* seq;                  // passes consumed so far (device counter)
+    int n_peers, my_rank, flag_pitch;
+    long long state_off;
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_update_fused(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0, int N, int XP,
+               const ExchangeParams x, long long* local, float* cent, double* cnorm, long long* state, int n_iter,
+               int32_t* n_active, const int32_t* __restrict__ run_pcol, __nv_bfloat16* __restrict__ C1,
+               __nv_bfloat16* __restrict__ C2, int NPK, volatile int32_t* mailbox) {
+    const int run = blockIdx.x;
+    long long* st = state + (long long)run * kStateWords;
+    __shared__ int s_go;
+    __shared__ long long s_cnt[LEIDA_KM_MAX_K];
+    const int K = run_k[run], crow0 = run_crow0[run];
+    const int AP = XP + 8;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool was_active = st[LEIDA_KM_ST_ACTIVE] != 0;        // block-uniform; only thread 0 writes it, later
+    const bool xchg = x.my_half != nullptr;
+    const long long acc0 = (long long)crow0 * AP;
+    if (xchg && was_active) {
+        const unsigned long long want = *x.seq + 1ull;
+        const longlong2* s2 = reinterpret_cast<const longlong2*>(local + acc0);       // AP is a multiple of 8 words
+        longlong2* d2 = reinterpret_cast<longlong2*>(x.my_half + acc0);
+        for (int i = threadIdx.x; i < K * AP / 2; i += blockDim.x) d2[i] = s2[i];
+        if (threadIdx.x < kStateWords)
+            x.my_half[x.state_off + (long long)run * kStateWords + threadIdx.x] =
+                local[x.state_off + (long long)run * kStateWords + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();            // the CTA's copies (ordered before this by the barrier) -> system scope
+            for (int p = 0; p < x.n_peers; ++p)
+                asm volatile("st.release.sys.global.u64 [%0], %1;"
+                             ::"l"(x.peer_flags[p] + (long long)x.my_rank * x.flag_pitch + run), "l"(want) : "memory");
+        }
+        if ((int)threadIdx.x < x.n_peers) {
+            const unsigned long long* f = x.flags_local + (long long)threadIdx.x * x.flag_pitch + run;
+            const long long t0 = clock64();
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v < want && clock64() - t0 > (20ll << 30)) __trap();     // ~10 s: a rank died; fail loudly
+            } while (v < want);
+        }
+        __syncthreads();
+    }
+    auto sum_word = [&](long long idx) -> long long {
+        if (!xchg) return local[idx];
+        if (x.mc) {
+            unsigned long long v;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(x.mc + idx) : "memory");
+            return (long long)v;
+        }
+        long long v = 0;
+        for (int p = 0; p < x.n_peers; ++p) v += *reinterpret_cast<const volatile long long*>(x.peers[p] + idx);
+        return v;
+    };
+    int my_empty = 0;
+    if (was_active && threadIdx.x < K) {
+        const long long c = sum_word(acc0 + (long long)threadIdx.x * AP + XP);
+        s_cnt[threadIdx.x] = c;
+        if (c <= 0) my_empty = 1;
+    }
+    long long changed = 0, rechecked = 0;
+    if (was_active && threadIdx.x == 0) {
+        changed = sum_word(x.state_off + (long long)run * kStateWords + LEIDA_KM_ST_CHANGED);
+        rechecked = sum_word(x.state_off + (long long)run * kStateWords + LEIDA_KM_ST_RECHECKED);
+    }
+    const int any_empty = __syncthreads_or(my_empty);
+    if (threadIdx.x == 0) {
+        int go = 0;
+        if (was_active) {
+            const long long p = st[LEIDA_KM_ST_PASSES];  // index of the pass that just finished
+            st[LEIDA_KM_ST_PASSES] = p + 1;
+            st[LEIDA_KM_ST_CHANGED_TOTAL] += changed;
+            st[LEIDA_KM_ST_RECHECK_TOTAL] += rechecked;
+            // pass p >= 1 is Lloyd iteration p-1; the reference tests convergence from iteration 1 on
+            // (clustering/_clustering.py:129-132) and runs at most n_iter iterations (:118).
+            if ((p >= 2 && changed == 0) || p >= n_iter) st[LEIDA_KM_ST_ACTIVE] = 0;
+            else go = 1;
+            if (go && any_empty) {
+                int e = 0;
+                for (int k = 0; k < K; ++k)
+                    if (s_cnt[k] <= 0) { e = k + 1; break; }
+                st[LEIDA_KM_ST_EMPTY] = e;
+                st[LEIDA_KM_ST_ACTIVE] = 0;
+                go = 0;
+            }
+            st[LEIDA_KM_ST_CHANGED] = 0;
+            st[LEIDA_KM_ST_RECHECKED] = 0;
+        }
+        s_go = go;
+        if (go) atomicAdd(n_active, 1);
+    }
+    __syncthreads();
+    if (s_go) {
+        const int pv = run_pcol ? run_pcol[run] : -1;      // packed column | slot width << 24 (k_plan)
+        const int pc = pv & 0xFFFFFF;
+        for (int k = w; k < K; k += 8) {
+            const long long row = acc0 + (long long)k * AP;
+            long long wv[CPL];
+            if (!xchg) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) { const int j = lane + 32 * c; wv[c] = j < N ? local[row + j] : 0; }
+            } else if (x.mc) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const int j = lane + 32 * c;
+                    unsigned long long v = 0;
+                    if (j < N)
+                        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(x.mc + row + j) : "memory");
+                    wv[c] = (long long)v;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) wv[c] = 0;
+                for (int p = 0; p < x.n_peers; ++p) {
+                    const long long* base = x.peers[p] + row;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        const int j = lane + 32 * c;
+                        if (j < N) wv[c] += *reinterpret_cast<const volatile long long*>(base + j);
+                    }
+                }
+            }
+            const double cnt = (double)s_cnt[k];
+            float v[CPL];
+            double ss = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int j = lane + 32 * c;
+                v[c] = j < N ? (float)(((double)wv[c] * (1.0 / kFracScale)) / cnt) : 0.f;
+                if (j < N) { const double d = (double)v[c]; ss += d * d; }
+                if (j < XP) cent[(long long)(crow0 + k) * XP + j] = v[c];
+            }
+            const double nrm = sqrt(warp_sum(ss));
+            if (lane == 0) cnorm[crow0 + k] = nrm;
+            if (pv >= 0) {
+                const float inv = nrm > 0.0 ? (float)(1.0 / nrm) : 0.f;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const int j = lane + 32 * c;
+                    if (j < XP && j < NPK) {
+                        const float u = v[c] * inv;                      // 0 for the bias column and the padding
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(u);
+                        C1[(long long)(pc + k) * NPK + j] = hi;
+                        C2[(long long)(pc + k) * NPK + j] = __float2bfloat16_rn(u - __bfloat162float(hi));
+                    }
+                }
+            }
+        }
+    }
+    // n_active[0] counts the runs that continue, n_active[1] the CTAs that have decided: the last one publishes
+    // {active runs, passes completed} to the host-visible mailbox and re-arms both (see k_update).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(&n_active[1], 1);
+        if (ticket == n_runs - 1) {
+            const int na = atomicAdd(&n_active[0], 0);
+            n_active[2] = na;
+            n_active[0] = 0;
+            n_active[1] = 0;
+            if (xchg) *x.seq += 1ull;               // every CTA has read it (all took a ticket)
+            if (mailbox) {
+                const int done = n_active[3] + 1;
+                n_active[3] = done;
+                if (na == 0 && n_active[4] == 0) n_active[4] = done;
+                const unsigned long long word = (unsigned long long)(na & 0xFFFF) | ((unsigned long long)(done & 0xFFFFFF) << 16) |
+                                                ((unsigned long long)(n_active[4] & 0xFFFFFF) << 40);
+                *reinterpret_cast<volatile unsigned long long*>(mailbox) = word;
+            }
+        }
+    }
+}
+
 // Distortion of every run: sum over rows of (1 - cos(row, assigned centroid))^2, fp64 per row,
 // accumulated as exact integers (2^-40 and 2^-80 words) so the result does not depend on the order
 // or on the number of GPUs.  One CTA = 32 rows x all runs: the rows are read ONCE (each warp keeps its
@@ -1239,6 +1435,42 @@ extern "C" int leida_kmeans_exchange_publish(int n_runs, const int32_t* run_k, c
         n_runs, run_k, run_crow0, (int)x_pitch + 8, (const long long*)local_words, (long long)n_acc_words,
         (long long*)exchange_half, (unsigned long long* const*)peer_flags, n_peers, my_rank, (unsigned long long*)seq, counter);
     return check_launch("k_exchange_publish");
+}
+
+extern "C" int leida_kmeans_update_fused(int n_runs, const int32_t* run_k, const int32_t* run_crow0, int N, int64_t x_pitch,
+                                         int64_t* local_words, int64_t state_offset_words, int64_t* exchange_half,
+                                         const int64_t* const* peer_halves, const int64_t* multicast_half,
+                                         uint64_t* const* peer_flags, const uint64_t* flags_local, int64_t flag_pitch,
+                                         int n_peers, int my_rank, uint64_t* seq, float* cent, double* cnorm,
+                                         int64_t* state, int n_iter, int32_t* n_active_out, const int32_t* run_pcol,
+                                         void* C1, void* C2, int32_t* mailbox, leida_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LEIDA_REQUIRE(run_k && run_crow0 && local_words && cent && cnorm && state && n_active_out, "null pointer");
+    int rc = check_runs(n_runs, N, x_pitch);
+    if (rc) return rc;
+    LEIDA_REQUIRE(n_iter >= 0 && state_offset_words > 0 && x_pitch <= 1024, "n_iter >= 0, x_pitch <= 1024");
+    LEIDA_REQUIRE((run_pcol == nullptr) == (C1 == nullptr) && (C1 == nullptr) == (C2 == nullptr), "run_pcol, C1, C2 together");
+    if (exchange_half) {
+        LEIDA_REQUIRE(peer_halves && peer_flags && flags_local && seq && n_peers >= 1 && n_peers <= 64 && my_rank >= 0 &&
+                          my_rank < n_peers && flag_pitch >= n_runs, "exchange arguments");
+    }
+    ExchangeParams x;
+    x.my_half = (long long*)exchange_half; x.peers = (const long long* const*)peer_halves;
+    x.mc = (const long long*)multicast_half; x.peer_flags = (unsigned long long* const*)peer_flags;
+    x.flags_local = (const unsigned long long*)flags_local; x.seq = (unsigned long long*)seq;
+    x.n_peers = n_peers; x.my_rank = my_rank; x.flag_pitch = (int)flag_pitch; x.state_off = (long long)state_offset_words;
+    const int NPK = (int)(((int64_t)N + 1 + 63) / 64 * 64);     // = leida_kmeans_tc_pitch(N)
+#define LEIDA_UF(CPLV)                                                                                                    \
+    k_update_fused<CPLV><<<n_runs, 256, 0, st>>>(n_runs, run_k, run_crow0, N, (int)x_pitch, x, (long long*)local_words, cent, \
+                                                 cnorm, (long long*)state, n_iter, n_active_out, run_pcol,               \
+                                                 (__nv_bfloat16*)C1, (__nv_bfloat16*)C2, NPK, mailbox)
+    if (x_pitch <= 128) LEIDA_UF(4);
+    else if (x_pitch <= 256) LEIDA_UF(8);
+    else if (x_pitch <= 416) LEIDA_UF(13);
+    else if (x_pitch <= 512) LEIDA_UF(16);
+    else LEIDA_UF(32);
+#undef LEIDA_UF
+    return check_launch("k_update_fused");
 }
 
 extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch, int n_runs,

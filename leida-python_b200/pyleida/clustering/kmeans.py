@@ -277,6 +277,32 @@ class KMeansEngine:
                         nv.ptr(plan), nv.ptr(prun), nv.ptr(run_k), nv.ptr(run_c0), nv.ptr(labels), nv.ptr(labels_new), nv.ptr(acc),
                         nv.ptr(state), stq)
                 timed("apply", f)
+            if fused and (self.comm.world == 1 or peers is not None):
+                # one kernel: [publish the run's words, raise / await the per-run flags, read sums over ranks,] means,
+                # norms and packed operands from registers
+                hkey = peers.half if peers is not None else 0
+                f = fast.get(("fused", stq, hkey))
+                if f is None:
+                    if peers is not None:
+                        half_ptr, ptrs, mc = peers.next_half()
+                        xargs = (half_ptr, nv.ptr(ptrs), mc or None, nv.ptr(peers._flag_ptrs), peers.flags_local,
+                                 peers.FLAG_PITCH, peers.world, peers.rank, peers.ctr.data_ptr() + 8)
+                    else:
+                        xargs = (None, None, None, None, None, 0, 1, 0, None)
+                    f = fast[("fused", stq, hkey)] = nv.prepared(
+                        "leida_kmeans_update_fused", R, nv.ptr(run_k), nv.ptr(run_c0), self.N, self.XP, nv.ptr(red_local),
+                        n_acc, *xargs, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(state), int(n_iter), nv.ptr(n_active),
+                        nv.ptr(run_pcol) if tc else None, nv.ptr(c1) if tc else None, nv.ptr(c2) if tc else None,
+                        mailbox.data_ptr(), stq)
+                elif peers is not None:
+                    peers.next_half()
+                timed("update", f)
+                if centroid_update == "reference":
+                    nv.call("leida_kmeans_means_f32_sequential", nv.ptr(self.X), self.M, self.N, self.XP, R, nv.ptr(run_k),
+                            nv.ptr(run_c0), nv.ptr(labels), nv.ptr(state), nv.ptr(cent), nv.ptr(cnorm), stq)
+                    if tc:
+                        tc_plan()                          # the float32 sequential means replace the centroids: re-pack
+                return
             if self.comm.world > 1 and peers is not None:
                 f = fast.get(("xchg", stq, peers.half))
                 if f is None:
@@ -313,6 +339,9 @@ class KMeansEngine:
                 if tc:
                     tc_plan()                          # the float32 sequential means replace the centroids: re-pack
 
+        # update + exchange in one kernel (rows up to 1024 columns, at most FLAG_PITCH runs when exchanging)
+        fused = self.XP <= 1024 and os.environ.get("LEIDA_UPDATE_LEGACY") is None and \
+            (peers is None or R <= PeerExchange.FLAG_PITCH)
         launches_per_pass = (3 if tc else 2 * len(groups)) + 1 + (2 if centroid_update == "reference" else 0)
         if tc:
             tc_plan()
@@ -406,7 +435,8 @@ class KMeansEngine:
         out.changed_total = int(st_host[:, nv.ST_CHANGED_TOTAL].sum())
         out.assign = assign
         out.exchange = ("none" if self.comm.world == 1 else "nccl all-reduce" if peers is None else
-                        "symmetric memory, multimem.ld_reduce" if peers.multicast else "symmetric memory, loads per rank")
+                        ("symmetric memory, multimem.ld_reduce" if peers.multicast else "symmetric memory, loads per rank") +
+                        (", fused into the update kernel (per-run flags)" if fused else ", publish + update kernels"))
         out.graph_launches = graph_launches
         out._acc = acc_red                    # exact fixed-point member sums (device), for centers_exact()
         return out

@@ -126,13 +126,15 @@ class PeerExchange:
     LEIDA_EXCHANGE = auto (default: symmetric memory when available) | peer (same, loads per rank even when multicast
     exists) | nccl.  Buffers are cached per (group, device) and reused by later engines."""
     _cache = {}
-    FLAG_WORDS = 64
+    FLAG_PITCH = 4096               # runs per batch that can be exchanged (one flag word per (rank, run))
 
     def __init__(self, words, dev, group, use_multicast=True):
         import torch
         import torch.distributed._symmetric_memory as symm
         self.words = int(words)
-        self.buf = symm.empty(2 * self.words + self.FLAG_WORDS, dtype=torch.int64, device=dev)
+        import torch.distributed as dist
+        self.flag_words = max(64, int(dist.get_world_size(group)) * self.FLAG_PITCH)
+        self.buf = symm.empty(2 * self.words + self.flag_words, dtype=torch.int64, device=dev)
         self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, group)
         self.world = int(self.hdl.world_size)
