@@ -215,6 +215,9 @@ int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, 
  *        tiles), a bound is 2*sum(K) + 128*12.  run_pcol[r] = first packed column | slot width << 24, or -1.  plan (2), tile_first/tile_count (c_rows/128), prun/pcol/run_pcol
  *        (n_runs): int32 device arrays owned by the caller, written by leida_kmeans_tc_plan. */
 int64_t leida_kmeans_tc_pitch(int N);
+/* packed centroid columns per tile of this build (128 or 256); c_rows must be a multiple, a bound on the packed columns
+ * is 4*sum(K) + 17 tiles */
+int leida_kmeans_tc_tile_columns(void);
 int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch, void* X1, void* X2,
                                leida_stream_t stream);
 int leida_kmeans_tc_plan(int n_runs, const int32_t* run_k, const int32_t* run_crow0, const int64_t* state,

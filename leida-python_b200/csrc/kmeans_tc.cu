@@ -21,14 +21,19 @@ namespace leida {
 
 constexpr int kStateWordsTc = LEIDA_KM_STATE_WORDS;
 constexpr int BM = 128;          // rows per tile  (UMMA M)
-constexpr int BN = 128;          // packed centroid columns per tile (UMMA N)
+#ifndef LEIDA_TC_BN
+#define LEIDA_TC_BN 128
+#endif
+constexpr int BN = LEIDA_TC_BN;  // packed centroid columns per tile (UMMA N): 128, or 256 (one MMA does twice the work)
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int ST = 3;            // smem pipeline stages
-constexpr int STAGE_BYTES = 4 * BM * BK * 2;          // X1, X2, C1, C2 blocks: 64 KB
+constexpr int ST = BN == 128 ? 3 : 2;                 // smem pipeline stages
+constexpr int A_BYTES = BM * BK * 2;                  // one bf16 block of the row tile: 16 KB
+constexpr int B_BYTES = BN * BK * 2;                  // one bf16 block of the column tile: 16 / 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // X1, X2, C1, C2 blocks: 64 / 96 KB
 constexpr int EPI_SPLIT = 4;                          // epilogue warps per TMEM lane quarter
 constexpr int EPI_WARPS = 4 * EPI_SPLIT;
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int N_ACC = 4;                              // fp32 accumulators of BN columns in flight (all 512 TMEM columns)
+constexpr int N_ACC = 512 / BN;                       // fp32 accumulators of BN columns in flight (all 512 TMEM columns)
 constexpr int TMEM_COLS = N_ACC * BN;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
@@ -328,9 +333,9 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
                         unsigned char* s = stages + stage * STAGE_BYTES;
                         mbar_expect_tx(&full[stage], STAGE_BYTES);
                         tma_load_2d(s, &tmX1, &full[stage], kb * BK, rt * BM);
-                        tma_load_2d(s + 16384, &tmX2, &full[stage], kb * BK, rt * BM);
-                        tma_load_2d(s + 32768, &tmC1, &full[stage], kb * BK, ct * BN);
-                        tma_load_2d(s + 49152, &tmC2, &full[stage], kb * BK, ct * BN);
+                        tma_load_2d(s + A_BYTES, &tmX2, &full[stage], kb * BK, rt * BM);
+                        tma_load_2d(s + 2 * A_BYTES, &tmC1, &full[stage], kb * BK, ct * BN);
+                        tma_load_2d(s + 2 * A_BYTES + B_BYTES, &tmC2, &full[stage], kb * BK, ct * BN);
                         if (++stage == ST) { stage = 0; phase ^= 1; }
                     }
         }
@@ -347,8 +352,8 @@ k_tc_assign(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CU
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         unsigned char* s = stages + stage * STAGE_BYTES;
-                        const uint64_t a1 = umma_desc(s), a2 = umma_desc(s + 16384);
-                        const uint64_t b1 = umma_desc(s + 32768), b2 = umma_desc(s + 49152);
+                        const uint64_t a1 = umma_desc(s), a2 = umma_desc(s + A_BYTES);
+                        const uint64_t b1 = umma_desc(s + 2 * A_BYTES), b2 = umma_desc(s + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             tc_mma_bf16(d, a1 + 2 * k, b1 + 2 * k, (kb | k) ? 1u : 0u);
@@ -468,10 +473,10 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
         // lives in registers and the per-class arrays (local memory: dynamic indexing) are touched only on a change.
         // ascending: the remainder of class c moves to the narrowest wider class whose part-filled tile can take it
         for (int c = 1; c < PLAN_CLASSES; ++c) {
-            const int cap = BN / (4 * c), rem = cnt[c] % cap;
+            const int cap = min(BN / (4 * c), 32), rem = cnt[c] % cap;
             if (rem == 0) continue;
             for (int d = c + 1; d < PLAN_CLASSES; ++d) {
-                const int capd = BN / (4 * d), remd = cnt[d] % capd;
+                const int capd = min(BN / (4 * d), 32), remd = cnt[d] % capd;
                 if (remd != 0 && remd + rem <= capd) { target[c] = d; cnt[c] -= rem; cnt[d] += rem; break; }
             }
         }
@@ -485,7 +490,7 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
             }
         };
         auto load = [&](int c) {
-            cc = c; c_stay = stay[c]; c_tile = cur_tile[c]; c_n = cur_n[c]; c_w = 4 * c; c_cap = BN / c_w;
+            cc = c; c_stay = stay[c]; c_tile = cur_tile[c]; c_n = cur_n[c]; c_w = 4 * c; c_cap = min(BN / c_w, 32);
         };
         for (int r = 0; r < n_runs; ++r) {
             const int c = s_cls[r];
@@ -782,12 +787,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D bf16 tensor (rows, NPK) row-major; box = 64 columns (128 B) x 128 rows, 128-byte swizzle.
-static int make_map(CUtensorMap* map, const void* ptr, long long rows, int NPK) {
+static int make_map(CUtensorMap* map, const void* ptr, long long rows, int NPK, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return LEIDA_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)NPK, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)NPK * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -801,6 +806,8 @@ static int make_map(CUtensorMap* map, const void* ptr, long long rows, int NPK) 
 using namespace leida;
 
 // columns of the bf16 operands: N features + 1 constant "bias" feature, rounded up to whole k-blocks
+extern "C" int leida_kmeans_tc_tile_columns(void) { return BN; }
+
 extern "C" int64_t leida_kmeans_tc_pitch(int N) { return ((int64_t)N + 1 + BK - 1) / BK * BK; }
 
 extern "C" int leida_kmeans_tc_split_rows(const float* X, int64_t M, int N, int64_t x_pitch, void* X1, void* X2,
@@ -858,22 +865,22 @@ extern "C" double leida_kmeans_tc_tau(int N) { return (double)default_tau((int)l
 
 namespace leida {
 // Tensor maps depend only on (device, base pointer, rows, pitch): the per-pass launches reuse them.
-struct MapKey { int dev; const void* ptr; long long rows; int npk; };
+struct MapKey { int dev; const void* ptr; long long rows; int npk; int box; };
 struct MapSlot { MapKey k; CUtensorMap m; bool used; };
 static MapSlot g_maps[32];
 static int g_map_next = 0;
 static std::mutex g_map_mu;
 static bool g_attr_set[64][2];
 
-static int cached_map(CUtensorMap* out, int dev, const void* ptr, long long rows, int npk) {
+static int cached_map(CUtensorMap* out, int dev, const void* ptr, long long rows, int npk, int box) {
     std::lock_guard<std::mutex> lk(g_map_mu);
     for (auto& s : g_maps)
-        if (s.used && s.k.dev == dev && s.k.ptr == ptr && s.k.rows == rows && s.k.npk == npk) { *out = s.m; return LEIDA_OK; }
+        if (s.used && s.k.dev == dev && s.k.ptr == ptr && s.k.rows == rows && s.k.npk == npk && s.k.box == box) { *out = s.m; return LEIDA_OK; }
     MapSlot& s = g_maps[g_map_next];
     g_map_next = (g_map_next + 1) % 32;
-    const int rc = make_map(&s.m, ptr, rows, npk);
+    const int rc = make_map(&s.m, ptr, rows, npk, box);
     if (rc) { s.used = false; return rc; }
-    s.k = MapKey{dev, ptr, rows, npk};
+    s.k = MapKey{dev, ptr, rows, npk, box};
     s.used = true;
     *out = s.m;
     return LEIDA_OK;
@@ -891,8 +898,8 @@ static int launch_tc_assign(const void* X1, const void* X2, const double* xnorm,
     LEIDA_CUDA_TRY(cudaGetDevice(&dev));
     CUtensorMap mx1, mx2, mc1, mc2;
     int rc;
-    if ((rc = cached_map(&mx1, dev, X1, M, NPK)) || (rc = cached_map(&mx2, dev, X2, M, NPK)) ||
-        (rc = cached_map(&mc1, dev, C1, c_rows, NPK)) || (rc = cached_map(&mc2, dev, C2, c_rows, NPK)))
+    if ((rc = cached_map(&mx1, dev, X1, M, NPK, BM)) || (rc = cached_map(&mx2, dev, X2, M, NPK, BM)) ||
+        (rc = cached_map(&mc1, dev, C1, c_rows, NPK, BN)) || (rc = cached_map(&mc2, dev, C2, c_rows, NPK, BN)))
         return rc;
     TcParams p;
     p.M = M; p.nkb = NPK / BK; p.plan = plan; p.tile_first = tile_first; p.tile_count = tile_count;

@@ -212,7 +212,8 @@ class KMeansEngine:
             x1, x2, npk = self._tc_operands()
             # packed columns: every run owns a slot of read_width(K) <= 2K columns; tiles hold one slot width each,
             # so up to one partly filled tile per width class
-            c_rows = (2 * CR + 128 * 12 + 127) // 128 * 128
+            bn = int(nv.lib.leida_kmeans_tc_tile_columns())
+            c_rows = (4 * CR + bn * 17 + bn - 1) // bn * bn
             c1 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
             c2 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
             labels_new = torch.empty((R, self.M), dtype=torch.int32, device=dev)

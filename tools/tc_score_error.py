@@ -31,7 +31,8 @@ def score_errors(eng, cent, ks, crow0):
     state = torch.zeros((R, nv.STATE_WORDS), dtype=torch.int64, device=dev)
     state[:, nv.ST_ACTIVE] = 1
     cnorm = cent[:, :N].double().norm(dim=1).contiguous()
-    c_rows = (2 * CR + 128 * 12 + 127) // 128 * 128
+    bn = int(nv.lib.leida_kmeans_tc_tile_columns())
+    c_rows = (4 * CR + bn * 17 + bn - 1) // bn * bn
     c1 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
     c2 = torch.zeros((c_rows, npk), dtype=torch.bfloat16, device=dev)
     plan = torch.zeros(2, dtype=torch.int32, device=dev)
