@@ -440,6 +440,14 @@ __global__ void k_split_rows(const float* __restrict__ X, long long M, int N, lo
 // One CTA: the run table is staged in shared memory with coalesced loads, thread 0 does the (inherently
 // sequential, a few cycles per run) placement, all threads write the result back.
 // run_pcol[r] = packed column | W << 24 (or -1); prun/pcol are ordered by (tile, column).
+// Runs a tile can hold for slot width w: the epilogue indexes a tile's runs by lane (<= 32) and reads whole chunks of
+// chunk_cols(w) columns, so the count is a multiple of the runs per chunk and no chunk reaches past the tile.
+__host__ __device__ constexpr int tile_capacity(int w) {
+    const int rpc = chunk_cols(w) / w;
+    int cap = BN / w;
+    if (cap > 32) cap = 32;
+    return cap / rpc * rpc;
+}
 constexpr int PLAN_MAX_RUNS = 4096;
 constexpr int PLAN_MAX_TILES = PLAN_MAX_RUNS / 2;   // widest slot = 64 columns = two runs per tile
 constexpr int PLAN_CLASSES = 17;              // slot width = 4 * class, classes 1..16
@@ -473,10 +481,10 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
         // lives in registers and the per-class arrays (local memory: dynamic indexing) are touched only on a change.
         // ascending: the remainder of class c moves to the narrowest wider class whose part-filled tile can take it
         for (int c = 1; c < PLAN_CLASSES; ++c) {
-            const int cap = min(BN / (4 * c), 32), rem = cnt[c] % cap;
+            const int cap = tile_capacity(4 * c), rem = cnt[c] % cap;
             if (rem == 0) continue;
             for (int d = c + 1; d < PLAN_CLASSES; ++d) {
-                const int capd = min(BN / (4 * d), 32), remd = cnt[d] % capd;
+                const int capd = tile_capacity(4 * d), remd = cnt[d] % capd;
                 if (remd != 0 && remd + rem <= capd) { target[c] = d; cnt[c] -= rem; cnt[d] += rem; break; }
             }
         }
@@ -490,7 +498,7 @@ k_plan(int n_runs, const int32_t* __restrict__ run_k, const long long* __restric
             }
         };
         auto load = [&](int c) {
-            cc = c; c_stay = stay[c]; c_tile = cur_tile[c]; c_n = cur_n[c]; c_w = 4 * c; c_cap = min(BN / c_w, 32);
+            cc = c; c_stay = stay[c]; c_tile = cur_tile[c]; c_n = cur_n[c]; c_w = 4 * c; c_cap = tile_capacity(c_w);
         };
         for (int r = 0; r < n_runs; ++r) {
             const int c = s_cls[r];
