@@ -21,6 +21,15 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a hung kernel must not hang the suite: pytest-timeout's thread method ends the process (a signal cannot
+        # interrupt a blocked CUDA call)
+        try:
+            import pytest_timeout  # noqa: F401
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(600, method="thread"))
+        except ImportError:
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -31,9 +31,11 @@ for stage in "$@"; do
     mbench4)   LEIDA_EXCHANGE=auto timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 3 --warmup 2 > $OUT/bench_4gpu_auto.json 2> $OUT/bench_4gpu_auto.err; echo "mbench4 rc=$?" ;;
     mconfig5)  LEIDA_EXCHANGE=auto timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $NG --config config5 --steps 1 --warmup 1 > $OUT/bench_config5_${NG}gpu.json 2> $OUT/bench_config5_${NG}gpu.err; echo "mconfig5 rc=$?" ;;
     bn256)     export LEIDA_B200_LIB=$PWD/leida-python_b200/pyleida/_lib/libleida_b200_bn256.so
-               timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py -m gpu -x -q -k "kmeans or tensor or config3 or config2 or tc_score or pipeline or smoke or identify" > $OUT/tests_bn256.log 2>&1; echo "tests bn256 rc=$?"
-               timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu --no-secondary > $OUT/bench_bn256.json 2> $OUT/bench_bn256.err; echo "bench bn256 rc=$?"
-               timeout 600 python bench.py --config config2 --steps 5 --warmup 3 --no-cpu --no-secondary > $OUT/bench_bn256_config2.json 2> $OUT/bench_bn256_config2.err; echo "bench bn256 config2 rc=$?"
+               timeout 150 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor_core_and_cuda_core or kmeans_golden or pipeline_golden" > $OUT/tests_bn256.log 2>&1; rc=$?; echo "tests bn256 rc=$rc"; tail -3 $OUT/tests_bn256.log
+               if [ $rc -eq 0 ]; then
+                 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu --no-secondary --no-e2e > $OUT/bench_bn256.json 2> $OUT/bench_bn256.err; echo "bench bn256 rc=$?"
+                 timeout 100 python bench.py --config config2 --steps 5 --warmup 3 --no-cpu --no-secondary --no-e2e > $OUT/bench_bn256_config2.json 2> $OUT/bench_bn256_config2.err; echo "bench bn256 config2 rc=$?"
+               fi
                unset LEIDA_B200_LIB ;;
     *) echo "unknown stage $stage" ;;
   esac
