@@ -477,7 +477,7 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
         "kernel": "k_tc_assign (tcgen05 bf16x3 distance GEMM of all active runs + top-2 epilogue)",
         "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak if tpeak else 0.0,
         "traffic": traffic,
-        "traffic_launch": "dram bytes of ONE full-width launch (all runs active), ncu --set full, profiles/",
+        "traffic_launch": "dram bytes of ONE full-width launch (all runs active), ncu --set full, profiles/r02_ncu_pass0.txt; the SURVEY per-run figure for that launch is n_runs x (4*M*N + 8*M) -- 549 GB at config 3 -- i.e. no re-reads: one pass over the rows serves every run",
         "peak_source": tsrc, "peak_burst": tburst, "frac_of_burst": ach / tburst if tburst else 0.0,
         "launches": n_assign, "avg_launch_ms": assign_ms / max(n_assign, 1),
         "share_of_step": assign_ms / (ms if ms > 0 else 1.0),
@@ -561,7 +561,8 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-width k_tc_assign launch (ncu --set full), per workload
-TRAFFIC_NCU = {"config2": 153.8e6}
+TRAFFIC_NCU = {"config2": 153.8e6,          # profiles/r01_k_tc_assign_ncu_full.txt, capture F
+               "config3": 3.603e9}          # profiles/r02_ncu_pass0.txt: 2.245 GB read (the bf16x2 rows once) + 1.358 GB written (labels)
 
 
 def native_arm(args):
