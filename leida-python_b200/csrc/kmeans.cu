@@ -730,9 +730,11 @@ k_update_fused(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __r
                 local[x.state_off + (long long)run * kStateWords + threadIdx.x];
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();            // the CTA's copies (ordered before this by the barrier) -> system scope
+            // release pattern: ONE system-scope fence (the CTA's copies are ordered before it by the barrier, and fences
+            // are cumulative), then a relaxed flag store per rank -- not a release store per rank, which is a fence each
+            __threadfence_system();
             for (int p = 0; p < x.n_peers; ++p)
-                asm volatile("st.release.sys.global.u64 [%0], %1;"
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;"
                              ::"l"(x.peer_flags[p] + (long long)x.my_rank * x.flag_pitch + run), "l"(want) : "memory");
         }
         if ((int)threadIdx.x < x.n_peers) {
