@@ -597,6 +597,9 @@ __device__ __forceinline__ long long quant40(float v) { return __double2ll_rn((d
 // is 0x4B400000 + the integer.  The bit patterns are summed as they are in 32-bit wrap-around arithmetic and
 // the offsets removed every 512 elements (|sum h| <= 2^29).  Same integers as quant40 (checked exhaustively
 // enough on the host: 2e8 random bit patterns and the tie / denormal / +-1 edge cases).
+#ifndef LEIDA_APPLY_GATHERS
+#define LEIDA_APPLY_GATHERS 8
+#endif
 // Four adjacent columns per thread (one 16-byte gather per listed row: a quarter of the row-index reads, address
 // products and load instructions of a column-per-thread loop -- the kernel is bound by instruction issue).
 // out[c] += sum over the listed rows of quant40(x[row][j4 + c]); when UNIT every element takes the FMA-pipe path.
@@ -614,15 +617,16 @@ __device__ __forceinline__ void quant_sum4(const float* __restrict__ xb, unsigne
         sl += __float_as_uint(tl);
     };
     int e = e0;
-    while (e + 3 * stride < e1) {
+    constexpr int G = LEIDA_APPLY_GATHERS;      // 16-byte gathers in flight per thread before the first value is used
+    while (e + (G - 1) * stride < e1) {
         uint32_t sh[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0}, nb = 0;
-        for (; nb < 128 && e + 3 * stride < e1; ++nb, e += 4 * stride) {
-            float4 v[4];
+        for (; nb < 512 / G && e + (G - 1) * stride < e1; ++nb, e += G * stride) {
+            float4 v[G];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < G; ++u)
                 v[u] = __ldg(reinterpret_cast<const float4*>(xb + ((unsigned)rows[e + u * stride] * XP + j4)));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < G; ++u) {
                 if (UNIT) {
                     // all four on the FMA pipe: with 16-byte gathers the conversion pipe (F2F + F2I.S64, 16 lanes per
                     // clock and SM) was what bound the dense passes when half of the elements still went through it
@@ -638,10 +642,11 @@ __device__ __forceinline__ void quant_sum4(const float* __restrict__ xb, unsigne
                 }
             }
         }
-        if (UNIT) {          // 4 * nb elements per column were summed with the offset in place (|sum h| <= 2^29)
+        if (UNIT) {          // G * nb <= 512 elements per column were summed with the offset in place (|sum h| <= 2^29)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                out[c] += ((long long)(int)(sh[c] - 4u * nb * MAGIC_BITS) << 20) + (long long)(int)(sl[c] - 4u * nb * MAGIC_BITS);
+                out[c] += ((long long)(int)(sh[c] - (uint32_t)G * nb * MAGIC_BITS) << 20) +
+                          (long long)(int)(sl[c] - (uint32_t)G * nb * MAGIC_BITS);
         }
     }
     for (; e < e1; e += stride) {

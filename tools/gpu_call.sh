@@ -37,6 +37,12 @@ for stage in "$@"; do
                  timeout 100 python bench.py --config config2 --steps 5 --warmup 3 --no-cpu --no-secondary --no-e2e > $OUT/bench_bn256_config2.json 2> $OUT/bench_bn256_config2.err; echo "bench bn256 config2 rc=$?"
                fi
                unset LEIDA_B200_LIB ;;
+    variant)   # A/B of a variant library (VARIANT=name) against the default build: kernel-level bench lines only
+               for lib in default $VARIANT; do
+                 if [ $lib = default ]; then unset LEIDA_B200_LIB; else export LEIDA_B200_LIB=$PWD/leida-python_b200/pyleida/_lib/libleida_b200_$lib.so; fi
+                 timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu --no-secondary --no-e2e > $OUT/bench_$lib.json 2> $OUT/bench_$lib.err; echo "bench $lib rc=$?"
+               done; unset LEIDA_B200_LIB ;;
+    driver)    timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $OUT/bench_driver.json 2> $OUT/bench_driver.err; echo "driver-style bench rc=$?" ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
