@@ -1476,31 +1476,26 @@ extern "C" int leida_kmeans_update_fused(int n_runs, const int32_t* run_k, const
 }
 
 extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch, int n_runs,
-                                       const int32_t* run_k, const int32_t* run_crow0, const float* cent,
+                                       int kmax, const int32_t* run_k, const int32_t* run_crow0, const float* cent,
                                        const double* cnorm, const int32_t* labels, int64_t* state,
                                        leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && labels && state, "null pointer");
     int rc = check_runs(n_runs, N, x_pitch);
     if (rc) return rc;
+    LEIDA_REQUIRE(kmax <= LEIDA_KM_MAX_K, "kmax <= 64 (0: unknown, use the gather kernel)");
     k_zero_dist<<<(n_runs + 127) / 128, 128, 0, st>>>((long long*)state, n_runs);
     if (M > 0) {
-        // tiled form when a run's centroids (double buffered) and the per-run sums fit in shared memory
-        int kmax = 0;
-        {
-            static thread_local std::vector<int32_t> hk;
-            hk.resize(n_runs);
-            LEIDA_CUDA_TRY(cudaMemcpyAsync(hk.data(), run_k, sizeof(int32_t) * n_runs, cudaMemcpyDeviceToHost, st));
-            LEIDA_CUDA_TRY(cudaStreamSynchronize(st));
-            for (int i = 0; i < n_runs; ++i) kmax = hk[i] > kmax ? hk[i] : kmax;
-        }
+        // tiled form when a run's centroids (staged in a ring) and the per-run sums fit in shared memory; kmax (the
+        // largest K of the batch) sizes the ring and comes from the caller, so the call stays asynchronous
         // ring depth: as deep as shared memory allows, 2..4 runs
         const size_t per_stage = (size_t)kmax * x_pitch * sizeof(float) + (size_t)kmax * sizeof(double);
         const size_t fixed2 = (size_t)n_runs * (2 * sizeof(unsigned long long) + 2 * sizeof(int)) + 64;
         int nst = 4;
         while (nst > 2 && nst * per_stage + fixed2 > (size_t)max_smem_optin()) --nst;
         const size_t smem2 = nst * per_stage + fixed2;
-        const bool tiled = x_pitch <= 512 && smem2 <= (size_t)max_smem_optin() && getenv("LEIDA_DISTORTION_LEGACY") == nullptr;
+        const bool tiled = kmax >= 1 && x_pitch <= 512 && smem2 <= (size_t)max_smem_optin() &&
+                           getenv("LEIDA_DISTORTION_LEGACY") == nullptr;
         if (tiled) {
 #define LEIDA_D2(CPLV, QV, NSTV)                                                                                          \
     do {                                                                                                                  \

@@ -60,7 +60,7 @@ SIGNATURES = {
     "leida_kmeans_update_fused": (c_int, [c_int, _P, _P, c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P,
                                           _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_exchange_publish": (c_int, [c_int, _P, _P, c_int64, _P, c_int64, _P, _P, c_int, c_int, _P, _P, _P]),
-    "leida_kmeans_distortion": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "leida_kmeans_distortion": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_means_f32_sequential": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_transform_f64": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, _P, _P]),
     "leida_remap_labels_i32": (c_int, [_P, c_int64, _P, c_int, _P]),

@@ -403,7 +403,7 @@ class KMeansEngine:
         launches = issued * launches_per_pass
         graph_launches = (issued - 1) * launches_per_pass if graphs is not None else 0   # not seen by the C-side counter
         timed("distortion", lambda: nv.call(
-            "leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
+            "leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, int(ks.max()), nv.ptr(run_k),
             nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), st))
         launches += 2
         if self.comm.world > 1:
