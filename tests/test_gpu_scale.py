@@ -270,3 +270,23 @@ def test_results_folder_binary_and_dataloader(P, tmp_path, monkeypatch):
         d = dl.centroids_distances(3)                       # KMeansLeida.transform on the GPU from the loaded model
         assert np.allclose(d.iloc[:, 2:].values, m.centroids_distances(3).iloc[:, 2:].values, atol=1e-6)
         assert type(dl.load_model(2)).__module__ == "pyleida.clustering._clustering"
+
+
+def test_legacy_update_and_distortion_kernels_agree(P, monkeypatch):
+    """The two-kernel update (LEIDA_UPDATE_LEGACY=1) and the gather distortion kernel (LEIDA_DISTORTION_LEGACY=1) stay
+    available as fallbacks (rows wider than 1024 / 512 columns, > 4096 runs): same labels, pass counts and centroids as
+    the fused update, inertia equal to the last bits' worth of a different fp64 summation order."""
+    from pyleida.clustering.kmeans import KMeansEngine
+    rng = np.random.default_rng(17)
+    X = rng.standard_normal((20_000, 150)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    eng = KMeansEngine(X)
+    runs = [(k, rng.choice(X.shape[0], size=k, replace=False).astype(np.int64)) for k in (3, 9, 20, 33)]
+    a = eng.run(runs, n_iter=25)
+    monkeypatch.setenv("LEIDA_UPDATE_LEGACY", "1")
+    monkeypatch.setenv("LEIDA_DISTORTION_LEGACY", "1")
+    b = eng.run(runs, n_iter=25)
+    for i in range(len(runs)):
+        assert bool((a.labels_device(i) == b.labels_device(i)).all()) and a.passes(i) == b.passes(i)
+        assert bool((a.centers_device(i) == b.centers_device(i)).all())
+        assert a.inertia(i) == pytest.approx(b.inertia(i), rel=1e-12)
