@@ -24,6 +24,9 @@ constexpr int BM = 128;          // rows per tile  (UMMA M)
 #ifndef LEIDA_TC_BN
 #define LEIDA_TC_BN 128
 #endif
+#ifndef LEIDA_MBAR_SUSPEND_NS
+#define LEIDA_MBAR_SUSPEND_NS 4000      // 0: plain polling (measured: assign 595 -> 573 ms per config-3 step with the hint)
+#endif
 constexpr int BN = LEIDA_TC_BN;  // packed centroid columns per tile (UMMA N): 128, or 256 (one MMA does twice the work)
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int ST = BN == 128 ? 3 : 2;                 // smem pipeline stages
@@ -54,14 +57,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     long long t0 = 0;
     for (unsigned spin = 0; !done; ++spin) {
+#if LEIDA_MBAR_SUSPEND_NS > 0
+        // suspend-time hint: the waiting warp sleeps in hardware until the phase completes (or the hint expires) instead
+        // of polling -- 16 epilogue warps poll 2e8 times per full-width launch otherwise
+        asm volatile(
+            "{\n.reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+            "selp.b32 %0, 1, 0, P1;\n}\n"
+            : "=r"(done) : "r"(addr), "r"(parity), "r"((uint32_t)LEIDA_MBAR_SUSPEND_NS) : "memory");
+#else
         asm volatile(
             "{\n.reg .pred P1;\n"
             "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
             "selp.b32 %0, 1, 0, P1;\n}\n"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#endif
         // A lost arrival must fail loudly, not hang the GPU -- but by TIME, not by poll count: preemption, MPS
         // time-slicing or a debugger can stretch a legitimate wait arbitrarily in polls.  ~20 s of SM clock.
+#if LEIDA_MBAR_SUSPEND_NS > 0
+        if (!done && (spin & 0x3FFu) == 0x3FFu) {
+#else
         if (!done && (spin & 0xFFFFFu) == 0xFFFFFu) {
+#endif
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > (40ll << 30)) __trap();
