@@ -92,3 +92,21 @@ def clustering_scores(engine, labels, ks, centroids64, sample_idx=None):
         cd[cd == 0] = np.inf
         db[c] = np.mean(np.max((intra[:, None] + intra[None, :]) / cd, axis=1))
     return {"Dunn_score": dunn, "silhouette_score": sil_h, "Davies-Bouldin_score": db}
+
+
+def dunn_fast(points, labels):
+    """Dunn index of a labelling on cosine distances (reference: clustering/_clustering.py:934-973): the smallest
+    non-zero distance between rows of different clusters over the largest distance between rows of the same cluster,
+    from one tiled pairwise pass on the GPU (the reference materialises the n x n matrix with sklearn).  `labels` may
+    be any values; they are ranked like np.unique does."""
+    torch = nv.require_cuda()
+    from .kmeans import KMeansEngine
+    pts = np.ascontiguousarray(np.asarray(points), dtype=np.float32)
+    uniq, lab = np.unique(np.asarray(labels), return_inverse=True)
+    if pts.ndim != 2 or lab.shape[0] != pts.shape[0]:
+        raise ValueError("'points' must be (N_samples, N_features) and 'labels' (N_samples,)")
+    eng = KMeansEngine(pts)
+    K = int(len(uniq))
+    cents = np.vstack([pts[lab == c].astype(np.float64).mean(0) for c in range(K)])
+    dev_labels = torch.from_numpy(lab.astype(np.int32)[None, :].copy()).to(eng.X.device)
+    return float(clustering_scores(eng, dev_labels, [K], [cents])["Dunn_score"][0])

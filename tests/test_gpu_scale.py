@@ -290,3 +290,13 @@ def test_legacy_update_and_distortion_kernels_agree(P, monkeypatch):
         assert bool((a.labels_device(i) == b.labels_device(i)).all()) and a.passes(i) == b.passes(i)
         assert bool((a.centers_device(i) == b.centers_device(i)).all())
         assert a.inertia(i) == pytest.approx(b.inertia(i), rel=1e-12)
+
+
+def test_dunn_fast_by_name(P, O):
+    """dunn_fast(points, labels) (clustering/_clustering.py:934-973) is exported under the reference's name."""
+    rng = np.random.default_rng(2)
+    cent = rng.standard_normal((4, 21))
+    lab = rng.integers(0, 4, 1500)
+    pts = (cent[lab] + 0.7 * rng.standard_normal((1500, 21))).astype(np.float32)
+    names = np.array([7, 3, 11, 20])[lab]                      # arbitrary label values
+    assert P.clustering.dunn_fast(pts, names) == pytest.approx(O.dunn_fast(pts, names), rel=2e-4)
