@@ -759,6 +759,43 @@ k_update_fused(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __r
         for (int p = 0; p < x.n_peers; ++p) v += *reinterpret_cast<const volatile long long*>(x.peers[p] + idx);
         return v;
     };
+    // The sums of a row: all CPL loads of a lane are issued before any is used; RB rows per warp are fetched together,
+    // and the first batch is requested BEFORE the counts and the continue / stop decision come back (the addresses do
+    // not depend on them), so a run that continues pays one memory round trip, not three.
+    constexpr int RB = CPL <= 8 ? 4 : CPL <= 13 ? 3 : CPL <= 16 ? 2 : 1;
+    auto load_row = [&](int k, long long* wv) {
+        const long long row = acc0 + (long long)k * AP;
+        if (!xchg) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) { const int j = lane + 32 * c; wv[c] = j < N ? local[row + j] : 0; }
+        } else if (x.mc) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int j = lane + 32 * c;
+                unsigned long long v = 0;
+                if (j < N)
+                    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(x.mc + row + j) : "memory");
+                wv[c] = (long long)v;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) wv[c] = 0;
+            for (int p = 0; p < x.n_peers; ++p) {
+                const long long* base = x.peers[p] + row;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const int j = lane + 32 * c;
+                    if (j < N) wv[c] += *reinterpret_cast<const volatile long long*>(base + j);
+                }
+            }
+        }
+    };
+    long long wv[RB][CPL];
+    if (was_active) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+            if (w + 8 * r < K) load_row(w + 8 * r, wv[r]);
+    }
     int my_empty = 0;
     if (was_active && threadIdx.x < K) {
         const long long c = sum_word(acc0 + (long long)threadIdx.x * AP + XP);
@@ -800,55 +837,39 @@ k_update_fused(int n_runs, const int32_t* __restrict__ run_k, const int32_t* __r
     if (s_go) {
         const int pv = run_pcol ? run_pcol[run] : -1;      // packed column | slot width << 24 (k_plan)
         const int pc = pv & 0xFFFFFF;
-        for (int k = w; k < K; k += 8) {
-            const long long row = acc0 + (long long)k * AP;
-            long long wv[CPL];
-            if (!xchg) {
+        for (int k0 = w; k0 < K; k0 += 8 * RB) {
+            if (k0 != w) {
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) { const int j = lane + 32 * c; wv[c] = j < N ? local[row + j] : 0; }
-            } else if (x.mc) {
+                for (int r = 0; r < RB; ++r)
+                    if (k0 + 8 * r < K) load_row(k0 + 8 * r, wv[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int k = k0 + 8 * r;
+                if (k >= K) break;
+                const double cnt = (double)s_cnt[k];
+                float v[CPL];
+                double ss = 0.0;
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
                     const int j = lane + 32 * c;
-                    unsigned long long v = 0;
-                    if (j < N)
-                        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(x.mc + row + j) : "memory");
-                    wv[c] = (long long)v;
+                    v[c] = j < N ? (float)(((double)wv[r][c] * (1.0 / kFracScale)) / cnt) : 0.f;
+                    if (j < N) { const double d = (double)v[c]; ss += d * d; }
+                    if (j < XP) cent[(long long)(crow0 + k) * XP + j] = v[c];
                 }
-            } else {
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) wv[c] = 0;
-                for (int p = 0; p < x.n_peers; ++p) {
-                    const long long* base = x.peers[p] + row;
+                const double nrm = sqrt(warp_sum(ss));
+                if (lane == 0) cnorm[crow0 + k] = nrm;
+                if (pv >= 0) {
+                    const float inv = nrm > 0.0 ? (float)(1.0 / nrm) : 0.f;
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) {
                         const int j = lane + 32 * c;
-                        if (j < N) wv[c] += *reinterpret_cast<const volatile long long*>(base + j);
-                    }
-                }
-            }
-            const double cnt = (double)s_cnt[k];
-            float v[CPL];
-            double ss = 0.0;
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int j = lane + 32 * c;
-                v[c] = j < N ? (float)(((double)wv[c] * (1.0 / kFracScale)) / cnt) : 0.f;
-                if (j < N) { const double d = (double)v[c]; ss += d * d; }
-                if (j < XP) cent[(long long)(crow0 + k) * XP + j] = v[c];
-            }
-            const double nrm = sqrt(warp_sum(ss));
-            if (lane == 0) cnorm[crow0 + k] = nrm;
-            if (pv >= 0) {
-                const float inv = nrm > 0.0 ? (float)(1.0 / nrm) : 0.f;
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const int j = lane + 32 * c;
-                    if (j < XP && j < NPK) {
-                        const float u = v[c] * inv;                      // 0 for the bias column and the padding
-                        const __nv_bfloat16 hi = __float2bfloat16_rn(u);
-                        C1[(long long)(pc + k) * NPK + j] = hi;
-                        C2[(long long)(pc + k) * NPK + j] = __float2bfloat16_rn(u - __bfloat162float(hi));
+                        if (j < XP && j < NPK) {
+                            const float u = v[c] * inv;                      // 0 for the bias column and the padding
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(u);
+                            C1[(long long)(pc + k) * NPK + j] = hi;
+                            C2[(long long)(pc + k) * NPK + j] = __float2bfloat16_rn(u - __bfloat162float(hi));
+                        }
                     }
                 }
             }
