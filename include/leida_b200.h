@@ -179,7 +179,10 @@ int leida_kmeans_assign(const float* X, const double* xnorm, int64_t M, int N, i
                         int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
                         const float* cent, const double* cnorm, int64_t* acc,
                         int32_t* labels, int64_t* state,
-                        int32_t* worklist, int64_t worklist_cap, leida_stream_t stream);
+                        int32_t* worklist, int64_t worklist_cap, int metric, leida_stream_t stream);
+/* metric: 0 = cosine distance (the LEiDA path), 1 = Euclidean distance -- KMeansLeida(metric='euclidean'),
+ * clustering/_clustering.py:61-75,111,127 (cdist(..., 'euclidean')): score = x.c - |c|^2/2, exact re-evaluation
+ * sqrt(sum (x - c)^2).  The tensor-core flow below is cosine only. */
 
 /* fp64 re-evaluation of the queued rows with the reference's arithmetic (scipy cdist 'cosine':
  * dot/(|u||v|), clip, 1-cos; first minimum) over the entry's candidate clusters (empty mask = all K: the
@@ -190,7 +193,8 @@ int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, 
                          int n_runs, const int32_t* run_k, const int32_t* run_crow0,
                          const float* cent, const double* cnorm, int64_t* acc,
                          int32_t* labels, int64_t* state,
-                         int32_t* worklist, int64_t worklist_cap, int32_t* labels_out, leida_stream_t stream);
+                         int32_t* worklist, int64_t worklist_cap, int32_t* labels_out, int metric,
+                         leida_stream_t stream);
 /* labels_out == NULL: the exact label replaces labels[run][row] and the row's contribution is moved
  * in acc (SIMT flow).  labels_out != NULL: the exact label is written to labels_out[run][row] only
  * (tensor-core flow; leida_kmeans_tc_apply does the moves).  In that flow a full queue is not an error:
@@ -322,7 +326,7 @@ int leida_kmeans_update_fused(int n_runs, const int32_t* run_k, const int32_t* r
 int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                             int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
                             const float* cent, const double* cnorm, const int32_t* labels,
-                            int64_t* state, leida_stream_t stream);
+                            int64_t* state, int metric, leida_stream_t stream);
 
 /* Reference-faithful centroid update (validation mode, single GPU): float32 row-after-row sums in
  * row order and a float32 divide, bit-identical to numpy's y[labels==c].mean(axis=0)
@@ -333,10 +337,10 @@ int leida_kmeans_means_f32_sequential(const float* X, int64_t M, int N, int64_t 
                                       float* cent, double* cnorm, leida_stream_t stream);
 
 /* KMeansLeida.transform / predict (clustering/_clustering.py:162-207): fp64 cosine distances of
- * rows to K centroids -> dist (M, K) (may be NULL) and/or labels (M) (may be NULL). */
+ * rows to K centroids -> dist (M, K) (may be NULL) and/or labels (M) (may be NULL); metric 0 = cosine, 1 = Euclidean. */
 int leida_kmeans_transform_f64(const float* X, int64_t M, int N, int64_t x_pitch,
                                const float* cent, int K, int64_t c_pitch,
-                               double* dist, int32_t* labels, leida_stream_t stream);
+                               double* dist, int32_t* labels, int metric, leida_stream_t stream);
 
 /* labels[i] = lut[labels[i]]  (KMeansLeida._remap_labels, clustering/_clustering.py:234-247;
  * the permutation itself is computed on the host with the reference's numpy calls). */

@@ -55,7 +55,23 @@ struct AssignParams {
     float tau0;
     int32_t* labels_out;  // recheck only: when set, write the exact label here and leave the move to the caller
     int n_runs;           // recheck only: runs to scan when the queue overflowed
+    int metric;           // 0: cosine distance (the LEiDA path), 1: Euclidean (KMeansLeida(metric='euclidean'), CUDA-core flow)
 };
+
+// Exact (fp64) distance of scipy's cdist for the two metrics the reference accepts (clustering/_clustering.py:61-75):
+// 'cosine' from the dot product and the norms, 'euclidean' = sqrt(sum (x - c)^2) from the squared difference.
+__device__ __forceinline__ double metric_distance(int metric, double acc, double xn, double cn) {
+    return metric ? sqrt(acc) : cosine_distance(acc, xn, cn);
+}
+__device__ __forceinline__ double seq_acc(int metric, const float* __restrict__ a, const float* __restrict__ b, int n) {
+    if (!metric) return dot_seq(a, b, n);
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double d = __dsub_rn((double)a[j], (double)b[j]);
+        s = __dadd_rn(s, __dmul_rn(d, d));
+    }
+    return s;
+}
 
 // Move one row's fixed-point contribution between clusters.  Called by `nthreads` cooperating
 // threads (`t` = index of the caller among them).
@@ -96,12 +112,22 @@ __global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
     const int nch = p.XP / 32;
     const float* cbase = p.cent + (long long)crow0 * p.XP;
 
-    if (tid == 0) s_nchg = 0;
+    __shared__ float s_cmax;
+    if (tid == 0) {
+        s_nchg = 0;
+        double m = 0.0;
+        if (p.metric)
+            for (int k = 0; k < K; ++k) m = fmax(m, p.cnorm[crow0 + k]);
+        s_cmax = (float)m * 1.0000002f;            // rounded up
+    }
     if (tid < KP) {
+        // cosine: score = dot / |c| (argmax); Euclidean: score = dot - |c|^2 / 2 (argmax == argmin of |x - c|^2)
         float ci = 0.f;
         if (tid < K) {
             const double cn = p.cnorm[crow0 + tid];
-            ci = cn > 0.0 ? (float)(1.0 / cn) : 0.f;
+            ci = p.metric ? (float)(-0.5 * cn * cn) : (cn > 0.0 ? (float)(1.0 / cn) : 0.f);
+        } else if (p.metric) {
+            ci = -INFINITY;
         }
         s_cinv[tid] = ci;
     }
@@ -176,13 +202,14 @@ __global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             if (k < K) {
-                const float s = acc[i][k] * s_cinv[k];
+                const float s = p.metric ? acc[i][k] + s_cinv[k] : acc[i][k] * s_cinv[k];
                 if (s > best) { second = best; best = s; bk = k; }
                 else if (s > second) second = s;
             }
         }
         const float xn = (float)p.xnorm[row];
-        const bool trusted = (best - second) > p.tau0 * xn;
+        // fp32 error of a score: cosine <= tau0/2 * |x|; Euclidean <= tau0/2 * (|x| |c| + |c|^2 / 2) with |c| <= cmax
+        const bool trusted = (best - second) > p.tau0 * (p.metric ? (xn * s_cmax + s_cmax * s_cmax) : xn);
         if (trusted) {
             const int old_l = lab[row];
             if (old_l != bk) {
@@ -204,7 +231,8 @@ __global__ void __launch_bounds__(128) k_assign(const AssignParams p) {
                 double bd = INFINITY;
                 int bkk = 0;
                 for (int k = 0; k < K; ++k) {
-                    const double d = cosine_distance(dot_seq(xr, cbase + (long long)k * p.XP, p.N), xnd, p.cnorm[crow0 + k]);
+                    const double d = metric_distance(p.metric, seq_acc(p.metric, xr, cbase + (long long)k * p.XP, p.N), xnd,
+                                                     p.cnorm[crow0 + k]);
                     if (d < bd) { bd = d; bkk = k; }
                 }
                 const int old_l = lab[row];
@@ -295,11 +323,17 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) s[u] = fma(xv[i], (double)cv[u][i], s[u]);
+                    for (int i = 0; i < RECHECK_MAX_COLS_PER_LANE; ++i) {
+                        if (p.metric) { const double d = xv[i] - (double)cv[u][i]; s[u] = fma(d, d, s[u]); }
+                        else s[u] = fma(xv[i], (double)cv[u][i], s[u]);
+                    }
             } else {
                 for (int u = 0; u < U; ++u) {
                     const float* cr = p.cent + (long long)(crow0 + ks[u]) * p.XP;
-                    for (int j = lane; j < p.N; j += 32) s[u] = fma((double)xr[j], (double)cr[j], s[u]);
+                    for (int j = lane; j < p.N; j += 32) {
+                        if (p.metric) { const double d = (double)xr[j] - (double)cr[j]; s[u] = fma(d, d, s[u]); }
+                        else s[u] = fma((double)xr[j], (double)cr[j], s[u]);
+                    }
                 }
             }
 #pragma unroll
@@ -308,7 +342,7 @@ __global__ void __launch_bounds__(128) k_recheck(const AssignParams p) {
             for (int u = 0; u < U; ++u) {
                 if (u < n) {
                     const int k = ks[u];
-                    const double d = cosine_distance(s[u], xn, p.cnorm[crow0 + k]);
+                    const double d = metric_distance(p.metric, s[u], xn, p.cnorm[crow0 + k]);
                     if (d != d && !any_nan) { any_nan = true; bd = -INFINITY; bk = k; }   // numpy argmin: first NaN wins
                     if (d < bd) { bd = d; bk = k; }
                 }
@@ -910,7 +944,7 @@ template <int CPL>
 __global__ void __launch_bounds__(256)
 k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long long M, int N, int XP, int n_runs,
              const int32_t* __restrict__ run_crow0, const float* __restrict__ cent,
-             const double* __restrict__ cnorm, const int32_t* __restrict__ labels, long long* state) {
+             const double* __restrict__ cnorm, const int32_t* __restrict__ labels, long long* state, int metric) {
     __shared__ int s_lab[DIST_RUN_CHUNK][DIST_ROWS];
     __shared__ unsigned long long s_hi[DIST_RUN_CHUNK], s_lo[DIST_RUN_CHUNK];
     __shared__ int s_c0[DIST_RUN_CHUNK];
@@ -970,11 +1004,17 @@ k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
 #pragma unroll
-                            for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) s4[u] = fma(xv[i], (double)cv[u][i], s4[u]);
+                            for (int i = 0; i < DIST_MAX_COLS_PER_LANE; ++i) {
+                                if (metric) { const double d = xv[i] - (double)cv[u][i]; s4[u] = fma(d, d, s4[u]); }
+                                else s4[u] = fma(xv[i], (double)cv[u][i], s4[u]);
+                            }
                     } else {
                         for (int u = 0; u < 4; ++u) {
                             const float* cr = cent + (long long)crow[u] * XP;
-                            for (int j = lane; j < N; j += 32) s4[u] = fma((double)xr[j], (double)cr[j], s4[u]);
+                            for (int j = lane; j < N; j += 32) {
+                                if (metric) { const double d = (double)xr[j] - (double)cr[j]; s4[u] = fma(d, d, s4[u]); }
+                                else s4[u] = fma((double)xr[j], (double)cr[j], s4[u]);
+                            }
                         }
                     }
 #pragma unroll
@@ -984,7 +1024,7 @@ k_distortion(const float* __restrict__ X, const double* __restrict__ xnorm, long
                     }
                 }
                 if (g0 + lane < gend) {
-                    const double d = cosine_distance(mine, xn, cnorm[mycrow]);
+                    const double d = metric_distance(metric, mine, xn, cnorm[mycrow]);
                     const double d2 = d * d * kFracScale;   // exact scaling
                     if (d2 == d2) {
                         const double f = floor(d2);
@@ -1241,10 +1281,10 @@ __global__ void k_cent_norms(const int32_t* __restrict__ run_k, const int32_t* _
     }
 }
 
-// transform / predict: warp per row, fp64.
+// transform / predict: warp per row, fp64; metric 0 = cosine, 1 = Euclidean (scipy cdist semantics).
 __global__ void __launch_bounds__(256)
 k_transform(const float* __restrict__ X, long long M, int N, long long XP, const float* __restrict__ cent, int K,
-            long long CP, double* dist, int32_t* labels) {
+            long long CP, double* dist, int32_t* labels, int metric) {
     const int lane = threadIdx.x & 31;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
@@ -1260,12 +1300,13 @@ k_transform(const float* __restrict__ X, long long M, int N, long long XP, const
         double s = 0.0, cc = 0.0;
         for (int j = lane; j < N; j += 32) {
             const double c = (double)cr[j];
-            s += (double)xr[j] * c;
+            if (metric) { const double d = (double)xr[j] - c; s += d * d; }
+            else s += (double)xr[j] * c;
             cc += c * c;
         }
         s = warp_sum(s);
         cc = sqrt(warp_sum(cc));
-        const double d = cosine_distance(s, xn, cc);
+        const double d = metric_distance(metric, s, xn, cc);
         if (dist && lane == 0) dist[row * K + k] = d;
         if (d != d && !any) { /* NaN: numpy argmin returns the first NaN */ bd = -INFINITY; bk = k; any = true; }
         if (d < bd) { bd = d; bk = k; }
@@ -1356,10 +1397,11 @@ extern "C" int leida_kmeans_init(const float* X_init, int64_t xi_pitch, const in
 extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                                    int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
                                         const float* cent, const double* cnorm, int64_t* acc, int32_t* labels,
-                                        int64_t* state, int32_t* worklist, int64_t worklist_cap,
+                                        int64_t* state, int32_t* worklist, int64_t worklist_cap, int metric,
                                         leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && acc && labels && state && worklist, "null pointer");
+    LEIDA_REQUIRE(metric == 0 || metric == 1, "metric: 0 cosine, 1 euclidean");
     int rc = check_runs(n_runs, N, x_pitch);
     if (rc) return rc;
     LEIDA_REQUIRE(kmax >= 2 && kmax <= LEIDA_KM_MAX_K, "2 <= kmax <= 64");
@@ -1369,7 +1411,7 @@ extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t 
     p.X = X; p.xnorm = xnorm; p.M = M; p.N = N; p.XP = (int)x_pitch;
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
-    p.worklist = worklist; p.worklist_cap = worklist_cap; p.labels_out = nullptr;
+    p.worklist = worklist; p.worklist_cap = worklist_cap; p.labels_out = nullptr; p.metric = metric;
     // fp32 error bound of score = fl(dot)*fl(1/|c|): (n+2) roundings of relative size 2^-24 on
     // sum |x_j c_j| <= |x||c|, doubled for the difference of two scores, 10% slack.
     p.tau0 = 2.2f * (float)(x_pitch + 8) * 5.9604645e-8f;
@@ -1389,15 +1431,17 @@ extern "C" int leida_kmeans_assign(const float* X, const double* xnorm, int64_t 
 extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                                     int n_runs, const int32_t* run_k, const int32_t* run_crow0, const float* cent,
                                     const double* cnorm, int64_t* acc, int32_t* labels, int64_t* state,
-                                    int32_t* worklist, int64_t worklist_cap, int32_t* labels_out,
+                                    int32_t* worklist, int64_t worklist_cap, int32_t* labels_out, int metric,
                                     leida_stream_t stream) {
     LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && acc && labels && state && worklist, "null pointer");
     LEIDA_REQUIRE(N >= 1 && x_pitch >= N && x_pitch % 32 == 0, "x_pitch multiple of 32 and >= N");
+    LEIDA_REQUIRE(metric == 0 || metric == 1, "metric: 0 cosine, 1 euclidean");
     AssignParams p;
     p.X = X; p.xnorm = xnorm; p.M = M; p.N = N; p.XP = (int)x_pitch;
     p.run_k = run_k; p.run_crow0 = run_crow0; p.cent = cent; p.cnorm = cnorm;
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
     p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out; p.n_runs = n_runs;
+    p.metric = metric;
     const int grid = sm_count() * (N > 256 ? 10 : 4);      // wide rows: more warps in flight hide the centroid loads
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 128) k_recheck<4><<<grid, 128, 0, st>>>(p);
@@ -1498,7 +1542,7 @@ extern "C" int leida_kmeans_update_fused(int n_runs, const int32_t* run_k, const
 
 extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch, int n_runs,
                                        int kmax, const int32_t* run_k, const int32_t* run_crow0, const float* cent,
-                                       const double* cnorm, const int32_t* labels, int64_t* state,
+                                       const double* cnorm, const int32_t* labels, int64_t* state, int metric,
                                        leida_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && labels && state, "null pointer");
@@ -1515,7 +1559,7 @@ extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int6
         int nst = 4;
         while (nst > 2 && nst * per_stage + fixed2 > (size_t)max_smem_optin()) --nst;
         const size_t smem2 = nst * per_stage + fixed2;
-        const bool tiled = kmax >= 1 && x_pitch <= 512 && smem2 <= (size_t)max_smem_optin() &&
+        const bool tiled = metric == 0 && kmax >= 1 && x_pitch <= 512 && smem2 <= (size_t)max_smem_optin() &&
                            getenv("LEIDA_DISTORTION_LEGACY") == nullptr;
         if (tiled) {
 #define LEIDA_D2(CPLV, QV, NSTV)                                                                                          \
@@ -1539,9 +1583,9 @@ extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int6
             return check_launch("k_distortion_tiled", 2);
         }
         const unsigned grid = (unsigned)((M + DIST_ROWS - 1) / DIST_ROWS);
-        if (N <= 128) k_distortion<4><<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state);
-        else if (N <= 256) k_distortion<8><<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state);
-        else k_distortion<0><<<grid, 256, 0, st>>>   /* wider rows: occupancy beats register residency (measured at N=400) */(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state);
+        if (N <= 128) k_distortion<4><<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state, metric);
+        else if (N <= 256) k_distortion<8><<<grid, 256, 0, st>>>(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state, metric);
+        else k_distortion<0><<<grid, 256, 0, st>>>   /* wider rows: occupancy beats register residency (measured at N=400) */(X, xnorm, M, N, (int)x_pitch, n_runs, run_crow0, cent, cnorm, labels, (long long*)state, metric);
     }
     return check_launch("k_distortion", M > 0 ? 2 : 1);
 }
@@ -1566,14 +1610,16 @@ extern "C" int leida_kmeans_means_f32_sequential(const float* X, int64_t M, int 
 }
 
 extern "C" int leida_kmeans_transform_f64(const float* X, int64_t M, int N, int64_t x_pitch, const float* cent, int K,
-                                          int64_t c_pitch, double* dist, int32_t* labels, leida_stream_t stream) {
+                                          int64_t c_pitch, double* dist, int32_t* labels, int metric,
+                                          leida_stream_t stream) {
     LEIDA_REQUIRE(X && cent, "null pointer");
+    LEIDA_REQUIRE(metric == 0 || metric == 1, "metric: 0 cosine, 1 euclidean");
     LEIDA_REQUIRE(dist || labels, "at least one output");
     LEIDA_REQUIRE(M >= 0 && N >= 1 && K >= 1 && x_pitch >= N && c_pitch >= N, "sizes");
     if (M == 0) return LEIDA_OK;
     const long long threads = M * 32;
     k_transform<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, M, N, x_pitch, cent, K, c_pitch,
-                                                                                     dist, labels);
+                                                                                     dist, labels, metric);
     return check_launch("k_transform");
 }
 

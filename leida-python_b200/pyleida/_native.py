@@ -45,8 +45,8 @@ SIGNATURES = {
     "leida_kmeans_pack_rows": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, _P]),
     "leida_kmeans_init": (c_int, [_P, c_int64, _P, c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P, c_int64, _P, _P]),
     "leida_kmeans_assign": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
-                                    c_int64, _P]),
-    "leida_kmeans_recheck": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P]),
+                                    c_int64, c_int, _P]),
+    "leida_kmeans_recheck": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int, _P]),
     "leida_kmeans_tc_pitch": (c_int64, [c_int]),
     "leida_kmeans_tc_tile_columns": (c_int, []),
     "leida_kmeans_tc_split_rows": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P]),
@@ -60,9 +60,9 @@ SIGNATURES = {
     "leida_kmeans_update_fused": (c_int, [c_int, _P, _P, c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P,
                                           _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "leida_kmeans_exchange_publish": (c_int, [c_int, _P, _P, c_int64, _P, c_int64, _P, _P, c_int, c_int, _P, _P, _P]),
-    "leida_kmeans_distortion": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "leida_kmeans_distortion": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "leida_kmeans_means_f32_sequential": (c_int, [_P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P]),
-    "leida_kmeans_transform_f64": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, _P, _P]),
+    "leida_kmeans_transform_f64": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int, c_int64, _P, _P, c_int, _P]),
     "leida_remap_labels_i32": (c_int, [_P, c_int64, _P, c_int, _P]),
     "leida_scores_cosine": (c_int, [_P, c_int64, c_int, _P, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "leida_scores_db": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, c_int, _P, _P, c_int, _P, _P]),

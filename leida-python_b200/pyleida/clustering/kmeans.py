@@ -115,7 +115,7 @@ class KMeansEngine:
         torch.cuda.current_stream().wait_stream(side)
         return graphs
 
-    def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1, profile=None, assign=None):
+    def run(self, runs, n_iter=1000, centroid_update="exact", poll_every=1, profile=None, assign=None, metric="cosine"):
         """runs: list of (k, init_rows) with init_rows = k global row indices.  Returns BatchResult.
         profile: optional dict; for every kernel name present as a key ("assign", "recheck", "apply",
         "update", "plan"; or all of them with {"*": True}) the (start, stop) CUDA event pairs bracketing
@@ -123,7 +123,12 @@ class KMeansEngine:
         torch = self.torch
         if centroid_update not in ("exact", "reference"):
             raise ValueError("centroid_update must be 'exact' or 'reference'")
+        if metric not in ("cosine", "euclidean"):
+            raise ValueError("'metric' must be either 'cosine' or 'euclidean'")
+        metric_id = 1 if metric == "euclidean" else 0
         assign = assign or DEFAULT_ASSIGN
+        if metric_id:
+            assign = "simt"                      # the tensor-core flow is cosine only
         if assign not in ("tc", "simt"):
             raise ValueError("assign must be 'tc' (tensor cores) or 'simt'")
         if centroid_update == "reference" and self.comm.world > 1:
@@ -255,11 +260,11 @@ class KMeansEngine:
                 nv.call("leida_kmeans_assign", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a, kmax,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
-                        nv.ptr(worklist), cap, stq)
+                        nv.ptr(worklist), cap, metric_id, stq)
                 nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
-                        nv.ptr(worklist), cap, None, stq)
+                        nv.ptr(worklist), cap, None, metric_id, stq)
 
         def do_rest():
             stq = st if not capturing[0] else nv.stream()
@@ -269,7 +274,7 @@ class KMeansEngine:
                     f = fast[("recheck", stq)] = nv.prepared(
                         "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
                         nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
-                        nv.ptr(worklist), cap, nv.ptr(labels_new), stq)
+                        nv.ptr(worklist), cap, nv.ptr(labels_new), 0, stq)
                 timed("recheck", f)
                 f = fast.get(("apply", stq, grid_bound[0]))
                 if f is None:
@@ -404,7 +409,7 @@ class KMeansEngine:
         graph_launches = (issued - 1) * launches_per_pass if graphs is not None else 0   # not seen by the C-side counter
         timed("distortion", lambda: nv.call(
             "leida_kmeans_distortion", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, int(ks.max()), nv.ptr(run_k),
-            nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), st))
+            nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(labels), nv.ptr(state), metric_id, st))
         launches += 2
         if self.comm.world > 1:
             red_global.copy_(red_local)
@@ -417,6 +422,8 @@ class KMeansEngine:
         hi = dist_words[:, 0].astype(np.float64)
         lo = dist_words[:, 1].astype(np.float64)
         inertia = hi * 2.0 ** -40 + lo * 2.0 ** -80
+        if metric_id:
+            inertia = inertia * self.scale ** 2          # squared Euclidean distances of the range-scaled rows
         inertia[dist_words[:, 0] >= (1 << 62)] = np.nan
         empty = st_host[:, nv.ST_EMPTY].copy()
         inertia[empty > 0] = np.nan
@@ -435,6 +442,7 @@ class KMeansEngine:
         out.rechecked_total = int(st_host[:, nv.ST_RECHECK_TOTAL].sum())
         out.changed_total = int(st_host[:, nv.ST_CHANGED_TOTAL].sum())
         out.assign = assign
+        out.metric = metric
         out.exchange = ("none" if self.comm.world == 1 else "nccl all-reduce" if peers is None else
                         ("symmetric memory, multimem.ld_reduce" if peers.multicast else "symmetric memory, loads per rank") +
                         (", fused into the update kernel (per-run flags)" if fused else ", publish + update kernels"))
@@ -442,13 +450,15 @@ class KMeansEngine:
         out._acc = acc_red                    # exact fixed-point member sums (device), for centers_exact()
         return out
 
-    def predict(self, centers):
-        """argmin cosine distance to `centers` (K, N) for every local row -> CUDA int32 (M,)."""
+    def predict(self, centers, metric="cosine"):
+        """argmin distance to `centers` (K, N) for every local row -> CUDA int32 (M,)."""
         torch = self.torch
         c = torch.as_tensor(np.ascontiguousarray(centers, dtype=np.float32)).to(self.X.device)
+        if metric == "euclidean" and self.scale != 1.0:
+            c = c * (1.0 / self.scale)                   # the rows are held range-scaled
         out = torch.empty(self.M, dtype=torch.int32, device=self.X.device)
         nv.call("leida_kmeans_transform_f64", nv.ptr(self.X), self.M, self.N, self.XP, nv.ptr(c), c.shape[0], c.shape[1],
-                None, nv.ptr(out), nv.stream())
+                None, nv.ptr(out), 1 if metric == "euclidean" else 0, nv.stream())
         return out
 
 
@@ -558,8 +568,8 @@ class KMeansLeida:
 
     Extra keyword arguments of fit(): init_indices (list of n_init index arrays, bypasses the
     legacy-RNG draw), centroid_update ('exact' | 'reference'), engine (reuse device
-    data).  metric='euclidean' is accepted by the constructor like the reference but only the
-    cosine path named by the north star is implemented.
+    data).  metric='cosine' (the LEiDA path) runs on the tensor cores; metric='euclidean' (accepted by the reference,
+    :61-75, never used by its pipeline) runs the CUDA-core assignment with the same fp64 re-check discipline.
     """
 
     def __init__(self, k=2, metric="cosine", n_init=10, n_iter=1_000):
@@ -575,8 +585,6 @@ class KMeansLeida:
         self._k_, self._metric_, self._n_iter_, self._n_init_ = k, metric, n_iter, n_init
 
     def fit(self, y, random_state=None, init_indices=None, centroid_update="exact", engine=None):
-        if self._metric_ != "cosine":
-            raise NotImplementedError("only metric='cosine' runs on the GPU path")
         eng = engine if engine is not None else KMeansEngine(y)
         M = eng.m_global
         if init_indices is not None:
@@ -593,7 +601,8 @@ class KMeansLeida:
             raise ValueError("init_indices must hold n_init index arrays")
         first = _dedupe(inits)
         uniq = sorted(set(first))
-        res = eng.run([(self._k_, inits[i]) for i in uniq], n_iter=self._n_iter_, centroid_update=centroid_update)
+        res = eng.run([(self._k_, inits[i]) for i in uniq], n_iter=self._n_iter_, centroid_update=centroid_update,
+                      metric=self._metric_)
         fitted = select_models(eng, res, {self._k_: [uniq.index(f) for f in first]}, self._n_init_)[self._k_]
         self.__dict__.update({k: v for k, v in fitted.__dict__.items() if k not in ("_k_", "_metric_", "_n_iter_", "_n_init_")})
         return self
@@ -621,22 +630,27 @@ class KMeansLeida:
             raise Exception("You have to fit the model first by using the 'fit' method.")
 
     def transform(self, y, closest=False):
-        """Cosine distances to the centroids, fp64 (clustering/_clustering.py:162-187)."""
+        """Distances to the centroids in the model's metric, fp64 (clustering/_clustering.py:162-187)."""
         self._check_is_fitted()
         torch = nv.require_cuda()
         eng = y if isinstance(y, KMeansEngine) else KMeansEngine(y, n_features=self.cluster_centers_.shape[1])
         c = torch.from_numpy(np.ascontiguousarray(self.cluster_centers_, dtype=np.float32)).to(eng.X.device)
+        euclid = self._metric_ == "euclidean"
+        if euclid and eng.scale != 1.0:
+            c = c * (1.0 / eng.scale)
         d = torch.empty((eng.M, c.shape[0]), dtype=torch.float64, device=eng.X.device)
         nv.call("leida_kmeans_transform_f64", nv.ptr(eng.X), eng.M, eng.N, eng.XP, nv.ptr(c), c.shape[0], c.shape[1],
-                nv.ptr(d), None, nv.stream())
+                nv.ptr(d), None, 1 if euclid else 0, nv.stream())
         d = d.cpu().numpy()
+        if euclid and eng.scale != 1.0:
+            d = d * eng.scale
         return d.min(1) if closest else d
 
     def predict(self, y):
         """Closest centroid of each row (clustering/_clustering.py:189-207)."""
         self._check_is_fitted()
         eng = y if isinstance(y, KMeansEngine) else KMeansEngine(y, n_features=self.cluster_centers_.shape[1])
-        return eng.predict(self.cluster_centers_).cpu().numpy().astype(np.int64)
+        return eng.predict(self.cluster_centers_, metric=self._metric_).cpu().numpy().astype(np.int64)
 
 
 # pickles of fitted models name the reference's module path (see clustering/_clustering.py in this package)

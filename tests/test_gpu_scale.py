@@ -300,3 +300,26 @@ def test_dunn_fast_by_name(P, O):
     pts = (cent[lab] + 0.7 * rng.standard_normal((1500, 21))).astype(np.float32)
     names = np.array([7, 3, 11, 20])[lab]                      # arbitrary label values
     assert P.clustering.dunn_fast(pts, names) == pytest.approx(O.dunn_fast(pts, names), rel=2e-4)
+
+
+@pytest.mark.parametrize("amp", [1.0, 250.0])
+def test_kmeans_euclidean_metric_vs_oracle(P, O, amp):
+    """KMeansLeida(metric='euclidean') (accepted by the reference, clustering/_clustering.py:61-75; cdist 'euclidean' at
+    :111,127,183,228): labels, centroids, inertia, transform and predict against the oracle (scipy cdist) -- on rows
+    inside [-1, 1] and on rows that need the engine's range scaling."""
+    rng = np.random.default_rng(31)
+    cent = rng.standard_normal((6, 40))
+    lab = rng.integers(0, 6, 8000)
+    X = ((cent[lab] + 0.8 * rng.standard_normal((8000, 40))) * 0.1 * amp).astype(np.float32)
+    for k in (3, 6, 11):
+        idx = [rng.choice(X.shape[0], size=k, replace=False) for _ in range(2)]
+        km = P.clustering.KMeansLeida(k=k, metric="euclidean", n_init=2).fit(X, init_indices=idx)
+        ref = O.KMeansLeida(k=k, metric="euclidean", n_init=2).fit(X, init_indices=idx)
+        assert np.array_equal(km.labels_, ref.labels_), (amp, k)
+        assert np.allclose(km.cluster_centers_, ref.cluster_centers_, rtol=0, atol=3e-6 * np.abs(ref.cluster_centers_).max())
+        assert km.inertia_ == pytest.approx(float(ref.inertia_), rel=1e-6)
+        Y = X[:500] + np.float32(0.01 * amp)
+        assert np.allclose(km.transform(Y), ref.transform(Y), rtol=1e-6, atol=1e-6 * amp)
+        assert np.array_equal(km.predict(Y), ref.predict(Y))
+    with pytest.raises(ValueError):
+        P.clustering.KMeansLeida(k=3, metric="manhattan")
