@@ -407,8 +407,8 @@ def test_kmeans_argument_errors(P):
         eng.run([(2, np.array([0, 50]))])                # index out of range
     with pytest.raises(ValueError):
         eng.run([(65, np.arange(65) % 50)])              # k <= 64
-    with pytest.raises(NotImplementedError):
-        P.clustering.KMeansLeida(k=2, metric="euclidean").fit(X)
+    with pytest.raises(ValueError):
+        eng.run([(2, np.array([0, 1]))], metric="manhattan")
     with pytest.raises(NotImplementedError):
         P.signal_tools.get_eigenvectors(np.zeros((4, 4, 3)), n=2)
 
