@@ -5,8 +5,10 @@
 // evaluated for every run at once).  fp32 operands are split into bf16 pairs (v = v1 + v2 + r,
 // |r| <= 2^-18 |v|) and the product is accumulated as X1*C1 + X1*C2 + X2*C1 in fp32 in TMEM, which
 // reproduces the fp32 product to ~2^-16 relative; the epilogue takes the top-2 scores per (row, run),
-// trusts the argmax only when the margin exceeds a conservative error bound (see leida_kmeans_tc_assign; the tensor core's internal fp32 accumulation is modelled, not documented) and queues the other rows for
-// the fp64 re-check (leida_kmeans_recheck), so labels are still the fp64 argmin of the reference.
+// trusts the argmax only when the margin exceeds the error bound (default_tau below: rigorous terms + the MEASURED
+// accumulation error of the tensor core, watched in production) and queues the other pairs -- with the set of
+// clusters that can still be the fp64 argmin -- for the fp64 re-check (leida_kmeans_recheck), so labels are still the
+// fp64 argmin of the reference.
 //
 // CTA = 18 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2..17 epilogue
 // (four per TMEM lane quarter).  Persistent over row tiles of 128 rows; for every row tile all column
