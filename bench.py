@@ -506,12 +506,26 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
         "distortion": ("k_distortion: fp64 distance of every row to its centroid, all runs; bytes = rows once + labels",
                        (4.0 * M_local * N + 4.0 * M_local * stats["n_runs"]) * steps),
     }
+    bounds = {"recheck": "latency / fp32->fp64 conversion pipe (ncu: profiles/r02_ncu_pass0.txt)",
+              "apply": "instruction issue in the dense passes (70 % of issue slots; the rows come from L2, hit rate 96 %)",
+              "update": "latency (one dependent round trip per pass)",
+              "distortion": "fp64 issue: conversions + shared-memory reads per FMA (profiles/r02_ncu_distortion.txt)"}
     kernels = {}
     for name, (what, nbytes) in models.items():
         if name in kernel_ms and kernel_ms[name] > 0:
-            kernels[name] = {"what": what, "ms_per_step": kernel_ms[name] / steps, "launches_per_step": kernel_n[name] / steps,
+            kernels[name] = {"what": what, "bound": bounds[name], "ms_per_step": kernel_ms[name] / steps,
+                             "launches_per_step": kernel_n[name] / steps,
                              "achieved_GBs": nbytes / (kernel_ms[name] * 1e-3) / 1e9,
                              "hbm_frac": nbytes / (kernel_ms[name] * 1e-3) / 1e9 / hpeak}
+    if "distortion" in kernels:
+        kernels["distortion"]["fp64_tflops"] = 2.0 * M_local * N * stats["n_runs"] * steps / (kernel_ms["distortion"] * 1e-3) / 1e12
+    if "stage12" in kernel_ms and kernel_ms["stage12"] > 0:
+        s12_bytes = (8.0 * (hi - lo) * N * wl["T"] + 8.0 * M_local * N + 4.0 * M_local * xp) * steps
+        kernels["stage12"] = {"what": "k_hilbert + k_eigvec_rank2 (fused stage 1+2); bytes = SURVEY 8d: 8*S*N*T in, 8*M*N + 4*M*NP out",
+                              "bound": "latency (fp64 FFT in shared memory: barriers and input loads; ncu: profiles/r02_ncu_stage12.txt)",
+                              "ms_per_step": kernel_ms["stage12"] / steps, "launches_per_step": kernel_n["stage12"] / steps,
+                              "achieved_GBs": s12_bytes / (kernel_ms["stage12"] * 1e-3) / 1e9,
+                              "hbm_frac": s12_bytes / (kernel_ms["stage12"] * 1e-3) / 1e9 / hpeak}
     for name in kernel_ms:
         if name not in models and name != "assign":
             kernels[name] = {"ms_per_step": kernel_ms[name] / steps, "launches_per_step": kernel_n[name] / steps}
