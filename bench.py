@@ -527,7 +527,7 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
                               "achieved_GBs": s12_bytes / (kernel_ms["stage12"] * 1e-3) / 1e9,
                               "hbm_frac": s12_bytes / (kernel_ms["stage12"] * 1e-3) / 1e9 / hpeak}
     for name in kernel_ms:
-        if name not in models and name != "assign":
+        if name not in models and name != "assign" and name not in kernels:
             kernels[name] = {"ms_per_step": kernel_ms[name] / steps, "launches_per_step": kernel_n[name] / steps}
     roofline["kernels"] = kernels
     roofline["other_kernels_ms_per_step"] = {k: v / steps for k, v in kernel_ms.items() if k != "assign"}
