@@ -194,8 +194,7 @@ int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t M, int N, 
                          const float* cent, const double* cnorm, int64_t* acc,
                          int32_t* labels, int64_t* state,
                          int32_t* worklist, int64_t worklist_cap, int32_t* labels_out, int metric,
-                         int n_runs_hint, leida_stream_t stream);
-/* n_runs_hint: an upper bound of the runs still active (0 = unknown); only sizes the grid. */
+                         leida_stream_t stream);
 /* labels_out == NULL: the exact label replaces labels[run][row] and the row's contribution is moved
  * in acc (SIMT flow).  labels_out != NULL: the exact label is written to labels_out[run][row] only
  * (tensor-core flow; leida_kmeans_tc_apply does the moves).  In that flow a full queue is not an error:

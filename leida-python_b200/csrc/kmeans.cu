@@ -1432,7 +1432,7 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
                                     int n_runs, const int32_t* run_k, const int32_t* run_crow0, const float* cent,
                                     const double* cnorm, int64_t* acc, int32_t* labels, int64_t* state,
                                     int32_t* worklist, int64_t worklist_cap, int32_t* labels_out, int metric,
-                                    int n_runs_hint, leida_stream_t stream) {
+                                    leida_stream_t stream) {
     LEIDA_REQUIRE(X && xnorm && run_k && run_crow0 && cent && cnorm && acc && labels && state && worklist, "null pointer");
     LEIDA_REQUIRE(N >= 1 && x_pitch >= N && x_pitch % 32 == 0, "x_pitch multiple of 32 and >= N");
     LEIDA_REQUIRE(metric == 0 || metric == 1, "metric: 0 cosine, 1 euclidean");
@@ -1442,9 +1442,7 @@ extern "C" int leida_kmeans_recheck(const float* X, const double* xnorm, int64_t
     p.acc = (long long*)acc; p.labels = labels; p.state = (long long*)state;
     p.worklist = worklist; p.worklist_cap = worklist_cap; p.tau0 = 0.f; p.labels_out = labels_out; p.n_runs = n_runs;
     p.metric = metric;
-    // wide rows: more warps in flight hide the centroid loads; few runs (the long tail of a sweep): a small grid, because
-    // with a handful of queued pairs the kernel's duration is the time to start and retire its CTAs
-    const int grid = sm_count() * (n_runs_hint > 0 && n_runs_hint <= 24 ? 1 : (N > 256 ? 10 : 4));
+    const int grid = sm_count() * (N > 256 ? 10 : 4);      // wide rows: more warps in flight hide the centroid loads
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 128) k_recheck<4><<<grid, 128, 0, st>>>(p);
     else if (N <= 256) k_recheck<8><<<grid, 128, 0, st>>>(p);

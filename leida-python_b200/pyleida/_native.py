@@ -46,7 +46,7 @@ SIGNATURES = {
     "leida_kmeans_init": (c_int, [_P, c_int64, _P, c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P, c_int64, _P, _P]),
     "leida_kmeans_assign": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                     c_int64, c_int, _P]),
-    "leida_kmeans_recheck": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int, c_int, _P]),
+    "leida_kmeans_recheck": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int, _P]),
     "leida_kmeans_tc_pitch": (c_int64, [c_int]),
     "leida_kmeans_tc_tile_columns": (c_int, []),
     "leida_kmeans_tc_split_rows": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, _P]),

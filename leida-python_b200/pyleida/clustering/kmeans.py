@@ -264,18 +264,17 @@ class KMeansEngine:
                 nv.call("leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, b - a,
                         run_k.data_ptr() + 4 * a, run_c0.data_ptr() + 4 * a, nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc),
                         labels.data_ptr() + 4 * a * self.M, state.data_ptr() + 8 * nv.STATE_WORDS * a,
-                        nv.ptr(worklist), cap, None, metric_id, 0, stq)
+                        nv.ptr(worklist), cap, None, metric_id, stq)
 
         def do_rest():
             stq = st if not capturing[0] else nv.stream()
             if tc:
-                small = 0 < grid_bound[0] <= 24          # few runs left: the re-check gets a small grid
-                f = fast.get(("recheck", stq, small))
+                f = fast.get(("recheck", stq))
                 if f is None:
-                    f = fast[("recheck", stq, small)] = nv.prepared(
+                    f = fast[("recheck", stq)] = nv.prepared(
                         "leida_kmeans_recheck", nv.ptr(self.X), nv.ptr(self.xnorm), self.M, self.N, self.XP, R, nv.ptr(run_k),
                         nv.ptr(run_c0), nv.ptr(cent), nv.ptr(cnorm), nv.ptr(acc), nv.ptr(labels), nv.ptr(state),
-                        nv.ptr(worklist), cap, nv.ptr(labels_new), 0, int(grid_bound[0]) if small else 0, stq)
+                        nv.ptr(worklist), cap, nv.ptr(labels_new), 0, stq)
                 timed("recheck", f)
                 f = fast.get(("apply", stq, grid_bound[0]))
                 if f is None:
