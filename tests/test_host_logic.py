@@ -82,3 +82,55 @@ def test_butterworth_design_matches_the_oracle():
     assert butterworth_design(1.0) is None
     with pytest.raises(ValueError):
         butterworth_design(1.0, low_pass=0.01, high_pass=0.1)
+
+
+def test_results_folder_binary_roundtrip_cpu(tmp_path):
+    """results_io writes the reference's layout (+ the binary copies) and pyleida.DataLoader reads it back -- file
+    access only, no GPU and no reference tree needed."""
+    import pickle
+    import pandas as pd
+    import pyleida
+    from pyleida import results_io
+    rng = np.random.default_rng(0)
+    M, N = 60, 5
+    subs = np.repeat(["s1", "s2", "s3"], 20)
+    conds = np.repeat(["A", "B", "A"], 20)
+    eig = pd.DataFrame(rng.standard_normal((M, N)), columns=[f"r{i}" for i in range(N)])
+    eig.insert(0, "subject_id", subs)
+    eig.insert(1, "condition", conds)
+    pred = pd.DataFrame({"subject_id": subs, "condition": conds, "k_2": rng.integers(0, 2, M), "k_3": rng.integers(0, 3, M)})
+    models = {}
+    for k in (2, 3):
+        km = pyleida.clustering.KMeansLeida(k=k)
+        km.cluster_centers_, km.labels_, km.inertia_, km._is_fitted = rng.standard_normal((k, N)).astype(np.float32), pred[f"k_{k}"].values, 1.0, True
+        models[f"k_{k}"] = km
+    perf = pd.DataFrame({"k": [2, 3], "Dunn_score": [0.1, 0.2], "distortion": [1.0, 0.5], "silhouette_score": [0.3, 0.2],
+                         "Davies-Bouldin_score": [1.0, 1.1]})
+    ids = pd.DataFrame({"subject_id": ["s1", "s3", "s2"], "condition": ["A", "A", "B"]})
+    dyn = {kind: {f"k_{k}": pd.concat([ids, pd.DataFrame(rng.random((3, k)), columns=[f"PL_state_{i + 1}" for i in range(k)])], axis=1)
+                  for k in (2, 3)} for kind in ("occupancies", "dwell_times")}
+    dyn["transitions"] = {f"k_{k}": pd.concat([ids, pd.DataFrame(rng.random((3, k * k)))], axis=1) for k in (2, 3)}
+    data = tmp_path / "data"
+    data.mkdir()
+    with open(data / "time_series.pkl", "wb") as f:
+        pickle.dump({s: rng.standard_normal((N, 22)) for s in ("s1", "s2", "s3")}, f)
+    with open(data / "metadata.pkl", "wb") as f:
+        pickle.dump({"s1": ["A"], "s2": ["B"], "s3": ["A"]}, f)
+    (data / "rois_labels.txt").write_text("\n".join(f"r{i}" for i in range(N)) + "\n")
+    for mode, kw in (("csv", {}), ("binary", dict(binary=True)), ("fast", dict(binary=True, csv=False))):
+        out = str(tmp_path / mode)
+        results_io.save_eigenvectors(out, eig, **kw)
+        results_io.save_clustering(out, pred, perf, models, **kw)
+        results_io.save_dynamics(out, dyn)
+        dl = pyleida.DataLoader(str(data), out)
+        got = dl.eigenvectors.iloc[:, 2:].values
+        assert np.allclose(got, eig.iloc[:, 2:].values, rtol=0, atol=0 if mode != "csv" else 1e-12)
+        assert list(dl.eigenvectors.columns) == list(eig.columns) and list(dl.eigenvectors.subject_id) == list(subs)
+        assert np.array_equal(dl.predictions["k_3"].values, pred["k_3"].values) and (dl._K_min_, dl._K_max_) == (2, 3)
+        assert np.array_equal(dl.load_model(2).cluster_centers_, models["k_2"].cluster_centers_)
+        assert dl.load_centroids(3).shape == (3, N) and dl.occupancies(2).shape == (3, 4) and dl.transitions(3).shape == (3, 11)
+        assert dl._classes_lst_ == ["A", "B"] and len(dl.time_series()) == 3
+        with pytest.raises(ValueError):
+            dl.load_model(7)
+    with pytest.raises(ValueError):
+        pyleida.DataLoader(str(data), str(tmp_path / "missing"))
