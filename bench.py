@@ -509,7 +509,9 @@ def measure(torch, dist, args, key, wl, steps, warmup, with_e2e=True, with_parit
     bounds = {"recheck": "latency / fp32->fp64 conversion pipe (ncu: profiles/r02_ncu_pass0.txt)",
               "apply": "instruction issue in the dense passes (70 % of issue slots; the rows come from L2, hit rate 96 %)",
               "update": "latency (one dependent round trip per pass)",
-              "distortion": "fp64 issue: conversions + shared-memory reads per FMA (profiles/r02_ncu_distortion.txt)"}
+              "distortion": "latency: 12 warps per SM (rows held in registers as doubles), per-(quad, run) reduction and "
+                            "label handling; the warps of a CTA share the staged centroids, so the slowest quad paces them "
+                            "(profiles/r02_ncu_distortion_piped.txt)"}
     kernels = {}
     for name, (what, nbytes) in models.items():
         if name in kernel_ms and kernel_ms[name] > 0:

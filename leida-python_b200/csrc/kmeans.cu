@@ -1222,6 +1222,276 @@ k_distortion_tiled(const float* __restrict__ X, const double* __restrict__ xnorm
     }
 }
 
+// ---- mbarrier / bulk-copy wrappers of the pipelined distortion kernel --------------------------------------------
+__device__ __forceinline__ uint32_t d3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d3_bar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d3_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void d3_bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(d3_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void d3_bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(d3_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void d3_bar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = d3_smem(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n.reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.b32 %0, 1, 0, P1;\n}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && (spin & 0xFFFFu) == 0xFFFFu) {        // a lost arrival fails loudly (by time, ~20 s of SM clock)
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (40ll << 30)) __trap();
+        }
+    }
+}
+// one contiguous block global -> shared through the bulk-copy engine; completion is counted in bytes on `bar`
+__device__ __forceinline__ void d3_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d3_smem(dst)), "l"(src), "r"(bytes), "r"(d3_smem(bar)) : "memory");
+}
+
+// Distortion, third form: the tiled kernel above spends its issue slots on everything but the FMAs (ncu, config 3:
+// 390 warp instructions per (quad, run), 104 of them the 52 DFMAs + their conversions; 16 % of the stall samples on
+// the block barrier of every run, staging by per-thread cp.async another ~60 instructions per thread and run).  Here
+//  * a run's centroids are ONE contiguous block of `cent` (K rows x XP floats): a single bulk copy issued by one
+//    thread stages them (the warps take turns), completion is counted on an mbarrier (`full`), and the ring is handed
+//    back through a second mbarrier (`empty`, one arrival per warp): no block barrier, warps drift apart by up to
+//    NST - 2 runs, and the ring keeps running across the tiles of a persistent CTA (the staged data does not depend on
+//    the tile);
+//  * the column bound is tested once (only the last 32-column group can be ragged), not per element;
+//  * a quad whose rows carry two distinct labels (in any arrangement: one transition inside four consecutive volumes,
+//    or a volume flickering between two neighbouring states) reads two centroid rows instead of four.
+// Arithmetic per row is exactly the tiled kernel's (same lane-strided fp64 FMA chain, same butterfly), so the sums are
+// bit-identical.
+// Tried and dropped: staging the centroids as doubles (converted once per launch) to take the float -> double
+// conversions out of the loop -- 64 KB per run leaves a three-deep ring without slack, and the kernel was 8 % slower.
+template <int CPL, int Q>
+__global__ void __launch_bounds__(D2_THREADS, 1)
+k_distortion_piped(const float* __restrict__ X, const double* __restrict__ xnorm, long long M, int XP, int n_runs,
+                   const int32_t* __restrict__ run_k, const int32_t* __restrict__ run_crow0,
+                   const float* __restrict__ cent, const double* __restrict__ cnorm, const int32_t* __restrict__ labels,
+                   long long* state, int kmax, int NST) {
+    constexpr int RPW = 4 * Q;                       // rows per warp
+    constexpr int ROWS = D2_WARPS * RPW;             // rows per tile
+    extern __shared__ __align__(128) unsigned char d3raw[];
+    const size_t stage_floats = ((size_t)kmax * XP + 31) / 32 * 32;                  // 128-byte multiples
+    float* cbuf = reinterpret_cast<float*>(d3raw);                                   // [NST][stage_floats] + 32 slack
+    double* cnb = reinterpret_cast<double*>(cbuf + (size_t)NST * stage_floats + 32); // [NST][kmax]
+    unsigned long long* s_hi = reinterpret_cast<unsigned long long*>(cnb + NST * kmax);   // [n_runs]
+    unsigned long long* s_lo = s_hi + n_runs;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_lo + n_runs);                     // [NST]
+    uint64_t* empty = full + NST;                                                    // [NST]
+    int* s_k = reinterpret_cast<int*>(empty + NST);                                  // [n_runs]
+    int* s_c0 = s_k + n_runs;                                                        // [n_runs]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < n_runs; i += D2_THREADS) {
+        s_hi[i] = 0; s_lo[i] = 0; s_k[i] = run_k[i]; s_c0[i] = run_crow0[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NST; ++b) { d3_bar_init(&full[b], 1); d3_bar_init(&empty[b], D2_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long n_tiles = (M + ROWS - 1) / ROWS;
+    const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total = my_tiles * n_runs;       // ring iterations of this CTA
+
+    // the calling warp stages a run into ring buffer b
+    auto stage = [&](int run, int b) {
+        const int K = s_k[run], crow0 = s_c0[run];
+        for (int i = lane; i < K; i += 32) cnb[b * kmax + i] = cnorm[crow0 + i];
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)K * (uint32_t)XP * 4u;
+            d3_bar_expect_tx(&full[b], bytes);
+            d3_bulk_g2s(cbuf + (size_t)b * stage_floats, cent + (long long)crow0 * XP, bytes, &full[b]);
+        }
+    };
+    // Iteration g stages iteration g + LEAD into the buffer iteration g - 1 - SLACK used: the staging warp then waits
+    // for a buffer every warp left SLACK iterations ago -- with SLACK = 0 it would wait for the slowest warp of the
+    // previous iteration, i.e. a block barrier in disguise (measured: a quarter of all stall samples)
+    const int SLACK = NST >= 5 ? 2 : (NST == 4 ? 1 : 0);
+    const int LEAD = NST - 1 - SLACK;
+    if (w == 0)
+        for (int g0 = 0; g0 < LEAD && g0 < total; ++g0) stage(g0 % n_runs, g0);
+
+    // CPL == ceil(XP / 32) (the launcher picks it so): only the last column group can be ragged
+    const bool last_in = lane + 32 * (CPL - 1) < XP;
+    const bool b4 = lane & 16, b3 = lane & 8;
+    const int u_mine = (b4 ? 2 : 0) + (b3 ? 1 : 0);          // the row of a quad this lane finishes
+    // ring iteration g = (tile index of this CTA) * n_runs + r uses buffer b = g % NST in its (g / NST)-th use (parity ph)
+    long long g = 0;
+    int b = 0;
+    uint32_t ph = 0;
+    int r_ahead = LEAD % n_runs;                     // run of iteration g + LEAD
+    int bt = 0;                                      // buffer (and parity pt) of iteration g - 1 - SLACK, once g > SLACK
+    uint32_t pt = 0;
+    int pw = 0;                                      // the warp that stages during iteration g: g % D2_WARPS -- the duty
+                                                     // (a dependent global load + the wait for the slowest warp) rotates,
+                                                     // a fixed producer warp would lag behind and pace the whole CTA
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * ROWS + (long long)w * RPW;
+        double xv[RPW][CPL];
+        double xn[RPW];
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const long long row = row0 + u;
+            const bool ok = row < M;
+            const float* xr = X + (ok ? row : 0) * XP;
+            xn[u] = ok ? xnorm[row] : 1.0;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int j = lane + 32 * i;
+                xv[u][i] = (ok && j < XP) ? (double)xr[j] : 0.0;
+            }
+        }
+        const bool lab_lane = lane < RPW && row0 + lane < M;
+        const int32_t* lab_ptr = labels + row0 + lane;
+        int lab_cur = lab_lane ? lab_ptr[0] : 0;
+        int lab_n1 = (lab_lane && 1 < n_runs) ? lab_ptr[(long long)M] : 0;
+        int lab_n2 = (lab_lane && 2 < n_runs) ? lab_ptr[2 * (long long)M] : 0;
+        const int32_t* lab_pf = lab_ptr + 3 * (long long)M;      // labels of run r + 3
+        double xn_q[Q], pend[Q], pend_cn[Q];
+#pragma unroll
+        for (int qd = 0; qd < Q; ++qd) {
+            xn_q[qd] = xn[4 * qd];
+#pragma unroll
+            for (int u = 1; u < 4; ++u) if (u_mine == u) xn_q[qd] = xn[4 * qd + u];
+            pend[qd] = 0.0;
+            pend_cn[qd] = 1.0;
+        }
+        for (int r = 0; r < n_runs; ++r, ++g) {
+            if (w == pw && g + LEAD < total) {
+                if (g > SLACK) d3_bar_wait(&empty[bt], pt);   // every warp has left iteration g - 1 - SLACK
+                stage(r_ahead, g > SLACK ? bt : (int)g + LEAD);
+            }
+            if (g > SLACK && ++bt == NST) { bt = 0; pt ^= 1u; }
+            if (++r_ahead == n_runs) r_ahead = 0;
+            if (++pw == D2_WARPS) pw = 0;
+            const int lab_n3 = (lab_lane && r + 3 < n_runs) ? *lab_pf : 0;
+            lab_pf += M;
+            d3_bar_wait(&full[b], ph);
+            const float* cb = cbuf + (size_t)b * stage_floats;
+#pragma unroll
+            for (int qd = 0; qd < Q; ++qd) {
+                int l[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    l[u] = __shfl_sync(0xffffffffu, lab_cur, 4 * qd + u);
+                    if (l[u] < 0) l[u] = 0;
+                }
+                double s[4] = {0.0, 0.0, 0.0, 0.0};
+                // two labels in the quad (any arrangement: row 0 carries `la`, bit u - 1 of MASK says row u carries the
+                // other one): two centroid rows serve the four rows; MASK = 0: one row serves all four
+                auto dots = [&](auto mtag, const float* ca, const float* cq) {
+                    constexpr int MASK = decltype(mtag)::value;
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) {
+                        const int j = lane + 32 * i;
+                        double va = (double)ca[j], vq = MASK ? (double)cq[j] : 0.0;
+                        if (i == CPL - 1) { va = last_in ? va : 0.0; vq = last_in ? vq : 0.0; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            s[u] = fma(xv[4 * qd + u][i], (u > 0 && ((MASK >> (u - 1)) & 1)) ? vq : va, s[u]);
+                    }
+                };
+                const int la = l[0];
+                const int lb = l[1] != la ? l[1] : (l[2] != la ? l[2] : l[3]);
+                const int mask = (l[1] != la ? 1 : 0) | (l[2] != la ? 2 : 0) | (l[3] != la ? 4 : 0);
+                const bool two = (l[1] == la || l[1] == lb) && (l[2] == la || l[2] == lb) && (l[3] == la || l[3] == lb);
+                const float* c0 = cb + (size_t)la * XP;
+                const float* c3 = cb + (size_t)l[3] * XP;
+                if (two) {
+                    const float* cq = cb + (size_t)lb * XP;
+                    switch (mask) {
+                        case 0: dots(std::integral_constant<int, 0>{}, c0, c0); break;
+                        case 1: dots(std::integral_constant<int, 1>{}, c0, cq); break;
+                        case 2: dots(std::integral_constant<int, 2>{}, c0, cq); break;
+                        case 3: dots(std::integral_constant<int, 3>{}, c0, cq); break;
+                        case 4: dots(std::integral_constant<int, 4>{}, c0, cq); break;
+                        case 5: dots(std::integral_constant<int, 5>{}, c0, cq); break;
+                        case 6: dots(std::integral_constant<int, 6>{}, c0, cq); break;
+                        default: dots(std::integral_constant<int, 7>{}, c0, cq); break;
+                    }
+                }
+                else {
+                    // four rows, four centroid rows: two rows at a time (two independent chains with few live
+                    // temporaries -- with all four in one loop the compiler runs the chains one after the other)
+                    const float* cr[4] = {c0, cb + (size_t)l[1] * XP, cb + (size_t)l[2] * XP, c3};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
+                            const int j = lane + 32 * i;
+                            double va = (double)cr[2 * h][j], vq = (double)cr[2 * h + 1][j];
+                            if (i == CPL - 1) { va = last_in ? va : 0.0; vq = last_in ? vq : 0.0; }
+                            s[2 * h] = fma(xv[4 * qd + 2 * h][i], va, s[2 * h]);
+                            s[2 * h + 1] = fma(xv[4 * qd + 2 * h + 1][i], vq, s[2 * h + 1]);
+                        }
+                    }
+                }
+                // four sums over 32 lanes with 6 shuffles (see k_distortion_tiled)
+                double a0 = b4 ? s[2] : s[0], a1 = b4 ? s[3] : s[1];
+                a0 += __shfl_xor_sync(0xffffffffu, b4 ? s[0] : s[2], 16);
+                a1 += __shfl_xor_sync(0xffffffffu, b4 ? s[1] : s[3], 16);
+                double t = b3 ? a1 : a0;
+                t += __shfl_xor_sync(0xffffffffu, b3 ? a0 : a1, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                int l_mine = l[0];
+#pragma unroll
+                for (int u = 1; u < 4; ++u) if (u_mine == u) l_mine = l[u];
+                const double cn_mine = cnb[b * kmax + l_mine];
+                if ((lane & 7) == (r & 7)) { pend[qd] = t; pend_cn[qd] = cn_mine; }
+            }
+            __syncwarp();                              // every lane's reads of the buffer are done
+            if (lane == 0) d3_bar_arrive(&empty[b]);
+            if ((r & 7) == 7 || r == n_runs - 1) {
+                const int my_run = (r & ~7) + (lane & 7);
+                unsigned long long hi = 0, lo = 0;
+#pragma unroll
+                for (int qd = 0; qd < Q; ++qd) {
+                    if (my_run <= r && row0 + 4 * qd + u_mine < M) {
+                        const double d = cosine_distance(pend[qd], xn_q[qd], pend_cn[qd]);
+                        const double d2 = d * d * kFracScale;   // exact scaling
+                        if (d2 == d2) {
+                            const double f = floor(d2);
+                            hi += (unsigned long long)(long long)f;
+                            lo += (unsigned long long)(long long)floor((d2 - f) * kFracScale);
+                        } else {
+                            hi += 0x4000000000000000ULL;        // poison: NaN distance
+                        }
+                    }
+                }
+                hi += __shfl_xor_sync(0xffffffffu, hi, 8);
+                lo += __shfl_xor_sync(0xffffffffu, lo, 8);
+                hi += __shfl_xor_sync(0xffffffffu, hi, 16);
+                lo += __shfl_xor_sync(0xffffffffu, lo, 16);
+                if (lane < 8 && my_run <= r && (hi | lo)) {
+                    atomicAdd(&s_hi[my_run], hi);
+                    atomicAdd(&s_lo[my_run], lo);
+                }
+            }
+            lab_cur = lab_n1; lab_n1 = lab_n2; lab_n2 = lab_n3;
+            if (++b == NST) { b = 0; ph ^= 1u; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_runs; i += D2_THREADS) {
+        if (s_hi[i] | s_lo[i]) {
+            atomic_add_ll(state + (long long)i * kStateWords + LEIDA_KM_ST_DIST_HI, (long long)s_hi[i]);
+            atomic_add_ll(state + (long long)i * kStateWords + LEIDA_KM_ST_DIST_LO, (long long)s_lo[i]);
+        }
+    }
+}
+
 __global__ void k_zero_dist(long long* state, int n_runs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n_runs) {
@@ -1561,6 +1831,36 @@ extern "C" int leida_kmeans_distortion(const float* X, const double* xnorm, int6
         const size_t smem2 = nst * per_stage + fixed2;
         const bool tiled = metric == 0 && kmax >= 1 && x_pitch <= 512 && smem2 <= (size_t)max_smem_optin() &&
                            getenv("LEIDA_DISTORTION_LEGACY") == nullptr;
+        // pipelined form (bulk copies + mbarriers): needs 16-byte aligned rows and CPL == ceil(x_pitch / 32)
+        const char* form = getenv("LEIDA_DISTORTION_FORM");           // "piped" (default) | "ring" (the cp.async form)
+        const bool want_piped = form == nullptr || form[0] != 'r';
+        if (tiled && want_piped && x_pitch % 4 == 0 && ((uintptr_t)cent & 15) == 0) {
+            const size_t stage_floats = ((size_t)kmax * x_pitch + 31) / 32 * 32;
+            const size_t per_stage3 = stage_floats * sizeof(float) + (size_t)kmax * sizeof(double) + 2 * sizeof(uint64_t);
+            const size_t fixed3 = fixed2 + 32 * sizeof(float) + 128;
+            int nst3 = 6;
+            while (nst3 > 2 && nst3 * per_stage3 + fixed3 > (size_t)max_smem_optin()) --nst3;
+            const size_t smem3 = nst3 * per_stage3 + fixed3;
+            if (smem3 <= (size_t)max_smem_optin()) {
+#define LEIDA_D3(CPLV, QV)                                                                                                \
+    case CPLV: {                                                                                                          \
+        const long long n_tiles = (M + D2_WARPS * 4 * QV - 1) / (D2_WARPS * 4 * QV);                                      \
+        const unsigned g3 = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());                                      \
+        LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_distortion_piped<CPLV, QV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+        k_distortion_piped<CPLV, QV><<<g3, D2_THREADS, smem3, st>>>(X, xnorm, M, (int)x_pitch, n_runs, run_k, run_crow0, cent, \
+                                                                    cnorm, labels, (long long*)state, kmax, nst3);        \
+    } break
+                switch ((int)((x_pitch + 31) / 32)) {
+                    LEIDA_D3(1, 3); LEIDA_D3(2, 3); LEIDA_D3(3, 3); LEIDA_D3(4, 3);
+                    LEIDA_D3(5, 2); LEIDA_D3(6, 2); LEIDA_D3(7, 2); LEIDA_D3(8, 2);
+                    LEIDA_D3(9, 1); LEIDA_D3(10, 1); LEIDA_D3(11, 1); LEIDA_D3(12, 1);
+                    LEIDA_D3(13, 1); LEIDA_D3(14, 1); LEIDA_D3(15, 1); LEIDA_D3(16, 1);
+                    default: LEIDA_REQUIRE(false, "k_distortion_piped: x_pitch out of range");
+                }
+#undef LEIDA_D3
+                return check_launch("k_distortion_piped", 2);
+            }
+        }
         if (tiled) {
 #define LEIDA_D2(CPLV, QV, NSTV)                                                                                          \
     do {                                                                                                                  \

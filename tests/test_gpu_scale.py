@@ -323,3 +323,34 @@ def test_kmeans_euclidean_metric_vs_oracle(P, O, amp):
         assert np.array_equal(km.predict(Y), ref.predict(Y))
     with pytest.raises(ValueError):
         P.clustering.KMeansLeida(k=3, metric="manhattan")
+
+
+@pytest.mark.parametrize("N", [40, 116, 150, 270, 400, 500])
+def test_distortion_forms_bit_identical(P, monkeypatch, N):
+    """The three forms of the distortion kernel (kmeans.cu: pipelined bulk-copy ring, cp.async ring, gather) use the same
+    per-row fp64 arithmetic: the exact-integer sums -- hence inertia_ -- are bit-identical between the two ring forms
+    and equal to the gather form's.  Rows with persistent labels (quads with one label / one transition) and rows with
+    unrelated labels (general path), a row count that is not a multiple of the tile, every column-group count class."""
+    from pyleida.clustering.kmeans import KMeansEngine
+    rng = np.random.default_rng(N)
+    M = 12_345
+    cent = rng.standard_normal((7, N))
+    seq = np.repeat(rng.integers(0, 7, M // 5 + 1), 5)[:M]               # dwell of 5 volumes: AAAB / AABB / ABBB quads
+    seq[M // 2:] = rng.integers(0, 7, M - M // 2)                         # second half: unrelated labels
+    X = (cent[seq] + 0.8 * rng.standard_normal((M, N))).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    eng = KMeansEngine(X)
+    runs = [(k, rng.choice(M, size=k, replace=False).astype(np.int64)) for k in (2, 5, 7, 12, 20, 3, 9, 16, 20)]
+    out = {}
+    for form in ("piped", "ring", "gather"):
+        monkeypatch.delenv("LEIDA_DISTORTION_LEGACY", raising=False)
+        if form == "gather":
+            monkeypatch.setenv("LEIDA_DISTORTION_LEGACY", "1")
+        else:
+            monkeypatch.setenv("LEIDA_DISTORTION_FORM", form)
+        res = eng.run(runs, n_iter=4)
+        out[form] = [res.inertia(i) for i in range(len(runs))]
+    # (a run that ends with an empty cluster has a NaN centroid and a NaN inertia in every form, like the reference)
+    assert np.array_equal(np.array(out["piped"]), np.array(out["ring"]), equal_nan=True)
+    np.testing.assert_allclose(out["piped"], out["gather"], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.isfinite(out["piped"]).sum() >= 5

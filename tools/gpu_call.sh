@@ -42,6 +42,14 @@ for stage in "$@"; do
                  if [ $lib = default ]; then unset LEIDA_B200_LIB; else export LEIDA_B200_LIB=$PWD/leida-python_b200/pyleida/_lib/libleida_b200_$lib.so; fi
                  timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu --no-secondary --no-e2e > $OUT/bench_$lib.json 2> $OUT/bench_$lib.err; echo "bench $lib rc=$?"
                done; unset LEIDA_B200_LIB ;;
+    final)     timeout 600 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/tests.log
+               timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"
+               timeout 600 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" ;;
+    dist_ab)   # same-box A/B of the two ring forms of the distortion kernel, alternating
+               timeout 200 python -m pytest tests/test_gpu_scale.py -m gpu -x -q -k distortion_forms > $OUT/tests_forms.log 2>&1; rc=$?; echo "forms rc=$rc"; tail -3 $OUT/tests_forms.log
+               [ $rc -eq 0 ] && for i in 1 2; do for f in ${FORMS:-piped ring}; do
+                 LEIDA_DISTORTION_FORM=$f timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu --no-secondary --no-e2e > $OUT/bench_${f}_$i.json 2> $OUT/bench_${f}_$i.err; echo "bench $f $i rc=$?"
+               done; done ;;
     driver)    timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $OUT/bench_driver.json 2> $OUT/bench_driver.err; echo "driver-style bench rc=$?" ;;
     *) echo "unknown stage $stage" ;;
   esac
