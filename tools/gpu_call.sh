@@ -42,6 +42,7 @@ for stage in "$@"; do
                  if [ $lib = default ]; then unset LEIDA_B200_LIB; else export LEIDA_B200_LIB=$PWD/leida-python_b200/pyleida/_lib/libleida_b200_$lib.so; fi
                  timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu --no-secondary --no-e2e > $OUT/bench_$lib.json 2> $OUT/bench_$lib.err; echo "bench $lib rc=$?"
                done; unset LEIDA_B200_LIB ;;
+    ncu_list_final) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 0 --no-cpu --no-secondary --no-e2e > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?" ;;
     final)     timeout 600 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/tests.log
                timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"
                timeout 600 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" ;;
