@@ -666,15 +666,18 @@ static int hilbert_launch(const double* x, int64_t n_series, int T, int64_t x_pi
     }
     int rc = check_launch("hilbert setup", direct ? 1 : 3);
     if (rc) return rc;
-    int per_sm = (int)((size_t)smem_max / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    // Persistent CTAs, exactly as many as are resident at once: shared memory would admit five 128-thread CTAs per SM at
+    // T = 1200, the register file four -- a grid sized by shared memory alone ran its last fifth as a second wave
+    // (4 group times instead of 3 for the 1600 pairs of a config-3 chunk).
     const long long n_groups = (n_pairs + batch - 1) / batch;
-    long long grid = (long long)sm_count() * per_sm;
-    if (grid > n_groups) grid = n_groups;
 #define LEIDA_HILBERT_LAUNCH(BL, CSV)                                                                                     \
     do {                                                                                                                  \
         LEIDA_CUDA_TRY(cudaFuncSetAttribute(k_hilbert<BL, CSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int per_sm = 0;                                                                                                   \
+        LEIDA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hilbert<BL, CSV>, threads, smem));        \
+        if (per_sm < 1) per_sm = 1;                                                                                       \
+        long long grid = (long long)sm_count() * per_sm;                                                                  \
+        if (grid > n_groups) grid = n_groups;                                                                             \
         k_hilbert<BL, CSV><<<(unsigned)grid, threads, smem, st>>>(x, n_series, T, x_pitch, out, out_pitch, t_begin,     \
                                                                   t_count, tw, plan, bt, batch);                         \
     } while (0)

@@ -43,6 +43,8 @@ for stage in "$@"; do
                  timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu --no-secondary --no-e2e > $OUT/bench_$lib.json 2> $OUT/bench_$lib.err; echo "bench $lib rc=$?"
                done; unset LEIDA_B200_LIB ;;
     ncu_list_final) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 0 --no-cpu --no-secondary --no-e2e > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?" ;;
+    quick)     timeout 60 python bench.py --steps 3 --warmup 2 --no-cpu --no-secondary --no-e2e > $OUT/bench_quick.json 2> $OUT/bench_quick.err; echo "bench rc=$?"
+               timeout 100 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/tests.log ;;
     final)     timeout 600 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/tests.log
                timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"
                timeout 600 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" ;;
