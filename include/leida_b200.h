@@ -321,8 +321,9 @@ int leida_kmeans_update_fused(int n_runs, const int32_t* run_k, const int32_t* r
 
 /* Distortion of every run against its final centroids (clustering/_clustering.py:209-232), fp64
  * per row, accumulated as exact integers into state[DIST_HI/LO].  kmax (host value): the largest K of the
- * batch -- it sizes the shared-memory ring of the tiled kernel (rows in registers, each run's centroids staged
- * once per 48-row tile; x_pitch <= 512); 0 selects the gather kernel. */
+ * batch -- it sizes the shared-memory ring of the tiled kernels (rows in registers, every run's centroids staged
+ * in shared memory by one bulk copy, a ring of up to six runs handed over through mbarriers; x_pitch <= 512 and a
+ * multiple of 4); 0 selects the gather kernel. */
 int leida_kmeans_distortion(const float* X, const double* xnorm, int64_t M, int N, int64_t x_pitch,
                             int n_runs, int kmax, const int32_t* run_k, const int32_t* run_crow0,
                             const float* cent, const double* cnorm, const int32_t* labels,
